@@ -1,0 +1,117 @@
+/* tspgnn.h -- C ABI of the B200-native TSP-GNN message-passing hot path.
+ *
+ * The reference (machine-reasoning-ufrgs/TSP-GNN) has no FFI: its boundary is the Python
+ * surface build_network(d) -> dict + sess.run(fetches, feed_dict) (model.py:9-170,
+ * train.py:25-42).  Each entry point below names the piece of that surface it replaces.
+ * tsp_gnn_b200/_lib.py binds them with ctypes; INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative TSPGNN_E_* code, with a human-readable message available from
+ * tspgnn_last_error() (thread-local).  `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream).  "host" pointers are ordinary (ideally pinned) host
+ * memory, "dev" pointers are device memory on the context's device.  Not re-entrant per
+ * handle; one handle per host thread / stream (the reference is single-session too).
+ */
+#ifndef TSPGNN_H_
+#define TSPGNN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tspgnn_ctx* tspgnn_handle;
+
+enum {
+  TSPGNN_OK = 0,
+  TSPGNN_E_INVALID = -1,   /* bad argument / shape (the reference raises Exception, graphnn.py:72-103,185-271) */
+  TSPGNN_E_CUDA = -2,      /* CUDA runtime error */
+  TSPGNN_E_STATE = -3,     /* call order violated (e.g. forward before plan / set_params) */
+  TSPGNN_E_UNSUPPORTED = -4
+};
+
+/* Arithmetic of the dense contractions.  State and all LayerNorm / gate math is fp32 in
+ * every mode.  */
+enum {
+  TSPGNN_MODE_SIMT_FP32 = 0,  /* fp32 FMA on CUDA cores (bring-up / cross-check path)            */
+  TSPGNN_MODE_TC_BF16X3 = 1,  /* tcgen05, operands split hi+lo bf16, 3 MMAs per product (fp32-parity mode) */
+  TSPGNN_MODE_TC_BF16 = 2     /* tcgen05, single bf16 MMA, bf16 embeddings / fp32 accumulate (BASELINE config 3) */
+};
+
+const char* tspgnn_last_error(void);
+int tspgnn_version(void);
+
+/* Number of float32 values in the parameter blob for embedding size d (115529 for d=64);
+ * order = tsp_gnn_b200/params.py:param_spec = the trainable variables of model.py:33-115. */
+int64_t tspgnn_param_count(int d);
+
+/* Replaces build_network(d) graph construction + tf.Session() (model.py:9, train.py:202-206).
+ * Only d == 64 (the reference default, train.py:108) is implemented.  */
+int tspgnn_create(int d, int mode, int device, tspgnn_handle* out);
+int tspgnn_destroy(tspgnn_handle h);
+int tspgnn_get_mode(tspgnn_handle h);
+
+/* Replaces tf.global_variables_initializer() / Saver.restore (train.py:210, util.py:17):
+ * uploads the flat fp32 blob (host pointer) and prepares the on-device operand images. */
+int tspgnn_set_params(tspgnn_handle h, const float* host_blob, int64_t n_floats);
+
+/* Replaces feeding the dense EV placeholder plus n_vertices / n_edges (model.py:20-23,
+ * instance_loader.py:45-67): edge row e has its two non-zeros in columns edge_src[e] <
+ * edge_dst[e] (global vertex ids); instance k owns edge rows [sum n_edges[:k], +n_edges[k])
+ * and vertex ids [sum n_vertices[:k], +n_vertices[k]).  Host pointers; copied to the device
+ * (inside the call) together with the derived CSR of EV^T.  Workspace is (re)allocated here. */
+int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_vertices, const int32_t* n_edges,
+                const int32_t* edge_src, const int32_t* edge_dst);
+
+/* Replaces sess.run(predictions, feed_dict={W, C, time_steps}) (train.py:25-42): host W,C
+ * [sumE] fp32 are copied in, the forward pass runs, logits/predictions [n_instances] fp32
+ * are copied back to host; synchronises `stream` before returning.  Either output may be NULL. */
+int tspgnn_forward_host(tspgnn_handle h, const float* W, const float* C, int time_steps,
+                        float* logits, float* predictions, void* stream);
+
+/* Same with W, C, logits, predictions in device memory; asynchronous on `stream`. */
+int tspgnn_forward_device(tspgnn_handle h, const float* dW, const float* dC, int time_steps,
+                          float* d_logits, float* d_predictions, void* stream);
+
+/* The three phases of the forward pass, separately (device pointers, asynchronous):
+ *   init_embeddings : model.py:33-51 + graphnn.py:134-139  (E0 = E_init_MLP([W,C]), V0, c = 0)
+ *   step            : n_steps iterations of while_body, graphnn.py:142-173 -- the unit the
+ *                     "message-passing timesteps/s" metric counts
+ *   readout         : model.py:107-147 (E_vote MLP, per-instance mean, sigmoid)            */
+int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const float* dC, void* stream);
+int tspgnn_step(tspgnn_handle h, int n_steps, void* stream);
+int tspgnn_readout(tspgnn_handle h, float* d_logits, float* d_predictions, void* stream);
+
+/* Replaces fetching last_states (model.py:123): row-major fp32 [sumV,64] / [sumE,64]
+ * device buffers; any pointer may be NULL.  Asynchronous on `stream`. */
+int tspgnn_get_states(tspgnn_handle h, float* dVh, float* dVc, float* dEh, float* dEc, void* stream);
+/* LSTM_initial_states / initial_embeddings of GraphNN.__call__ (graphnn.py:128,134-139):
+ * overwrite the recurrent state from row-major fp32 device buffers (NULL = leave as is). */
+int tspgnn_set_states(tspgnn_handle h, const float* dVh, const float* dVc, const float* dEh,
+                      const float* dEc, void* stream);
+
+/* Sizes of the current plan. */
+int64_t tspgnn_sum_edges(tspgnn_handle h);
+int64_t tspgnn_sum_vertices(tspgnn_handle h);
+
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int64_t tspgnn_launch_count(tspgnn_handle h);
+
+/* Measurement hook for bench.py's roofline line: launches ONE kernel of the timestep
+ * `iters` times on `stream`, each launch bracketed by CUDA events, and returns the mean
+ * duration in milliseconds.  which: 0 = LayerNorm-LSTM kernel (K1), 1 = message-MLP kernel
+ * (K2).  Tensor-core modes only.  The recurrent state keeps evolving while this runs. */
+int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* mean_ms, void* stream);
+
+/* Host helper: dense EV (row-major [rows, cols], float64 or float32 by elem_size 8/4) ->
+ * edge_src/edge_dst (instance_loader.py:63-66 layout).  Returns TSPGNN_E_INVALID if a row
+ * does not have exactly two non-zeros. */
+int tspgnn_dense_ev_to_coo(const void* EV, int elem_size, int64_t rows, int64_t cols,
+                           int32_t* edge_src, int32_t* edge_dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSPGNN_H_ */

@@ -1,0 +1,48 @@
+"""Generates the golden fixtures of tests/golden/ from the float64 oracle.
+
+    python tests/golden/make_golden.py
+
+The reference itself cannot run here (TensorFlow 1.x is not installable offline), so these
+vectors pin the oracle and the CUDA path against *regressions* and travel to the GPU box;
+they are not outputs of the reference (parity unpinned, see oracle/tspgnn_oracle.py).
+Inputs are regenerated from seeds by the tests; only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import tspgnn_oracle as orc          # noqa: E402
+from tsp_gnn_b200 import instances as inst      # noqa: E402
+
+CASES = {
+    # name: (sizes, instance seed, param seed, perturb_ln, time_steps, connectivity)
+    "tiny_mixed": ([5, 6, 7, 8], 11, 7, True, 4, 1.0),
+    "config1_16x20": ([20] * 16, 42, 0, False, 32, 1.0),
+    "sparse_mixed": ([9, 12, 10], 5, 3, True, 6, 0.5),
+    "tail_tiles": ([17, 3, 18], 23, 9, True, 3, 1.0),
+}
+
+
+def run_case(name):
+    sizes, iseed, pseed, perturb, T, conn = CASES[name]
+    EV, W, C, y, nv, ne = inst.synth_batch(sizes, seed=iseed, connectivity=conn)
+    params = orc.init_params(64, seed=pseed, perturb_ln=perturb)
+    out = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, T, dtype=np.float64)
+    return out
+
+
+if __name__ == "__main__":
+    here = os.path.dirname(os.path.abspath(__file__))
+    store = {}
+    for name in CASES:
+        out = run_case(name)
+        store[name + "/logits"] = out["logits"]
+        store[name + "/predictions"] = out["predictions"]
+        store[name + "/E_h_rowsum"] = out["E_h"].sum(axis=1)
+        store[name + "/V_h"] = out["V_h"] if out["V_h"].shape[0] <= 64 else out["V_h"][:64]
+        store[name + "/E_c_head"] = out["E_c"][:32]
+    np.savez_compressed(os.path.join(here, "golden_forward.npz"), **store)
+    print("wrote", os.path.join(here, "golden_forward.npz"), {k: v.shape for k, v in store.items()})

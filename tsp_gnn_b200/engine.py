@@ -1,0 +1,142 @@
+"""Thin object wrapper over the C ABI: one Engine = one tspgnn_handle on one GPU.
+
+PyTorch is used only as the device-memory / stream container; every compute call goes
+through libtspgnn.so.  There is no CPU fallback.
+"""
+import ctypes
+import numpy as np
+
+from . import _lib
+from .params import flatten, param_offsets
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine(object):
+    def __init__(self, d=64, mode="bf16x3", device=0):
+        self.d = d
+        self.mode = mode
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib.tspgnn_create(d, _lib.MODES[mode], self.device, ctypes.byref(h)))
+        self._h = h
+        self._stream = None
+        self.B = 0
+        self.n_edges_total = 0
+        self.n_vertices_total = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib.tspgnn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------
+    def stream(self):
+        """A dedicated (non-legacy) torch stream so the timestep loop can be graph-captured."""
+        if self._stream is None:
+            import torch
+            self._stream = torch.cuda.Stream(device=self.device)
+        return self._stream
+
+    def _sptr(self, stream=None):
+        s = stream if stream is not None else self.stream()
+        return ctypes.c_void_p(s.cuda_stream)
+
+    # -- parameters / plan --------------------------------------------------------
+    def set_params(self, params):
+        blob = params if isinstance(params, np.ndarray) else flatten(params, self.d)
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        _lib.check(_lib.lib.tspgnn_set_params(self._h, _np_ptr(blob), blob.size))
+
+    def plan(self, n_vertices, n_edges, edge_src, edge_dst):
+        nv = np.ascontiguousarray(n_vertices, dtype=np.int32)
+        ne = np.ascontiguousarray(n_edges, dtype=np.int32)
+        src = np.ascontiguousarray(edge_src, dtype=np.int32)
+        dst = np.ascontiguousarray(edge_dst, dtype=np.int32)
+        if nv.shape != ne.shape or nv.ndim != 1:
+            raise ValueError("n_vertices and n_edges must be 1-D arrays of equal length")
+        if src.shape != dst.shape or src.ndim != 1 or src.shape[0] != int(ne.sum()):
+            raise ValueError("edge_src/edge_dst must have sum(n_edges) entries")
+        _lib.check(_lib.lib.tspgnn_plan(self._h, nv.shape[0], _np_ptr(nv), _np_ptr(ne), _np_ptr(src), _np_ptr(dst)))
+        self.B = int(nv.shape[0])
+        self.n_edges_total = int(ne.sum())
+        self.n_vertices_total = int(nv.sum())
+
+    # -- forward ------------------------------------------------------------------
+    def forward_host(self, W, C, time_steps, stream=None):
+        """Host numpy in, host numpy out (H2D + forward + D2H inside the call)."""
+        W = np.ascontiguousarray(np.asarray(W, dtype=np.float32).reshape(-1))
+        C = np.ascontiguousarray(np.asarray(C, dtype=np.float32).reshape(-1))
+        if W.shape[0] != self.n_edges_total or C.shape[0] != self.n_edges_total:
+            raise ValueError("W and C must have sum(n_edges)=%d rows" % self.n_edges_total)
+        logits = np.empty(self.B, dtype=np.float32)
+        preds = np.empty(self.B, dtype=np.float32)
+        _lib.check(_lib.lib.tspgnn_forward_host(self._h, _np_ptr(W), _np_ptr(C), int(time_steps), _np_ptr(logits),
+                                                _np_ptr(preds), self._sptr(stream)))
+        return logits, preds
+
+    def forward_device(self, dW, dC, time_steps, d_logits, d_preds, stream=None):
+        _lib.check(_lib.lib.tspgnn_forward_device(self._h, ctypes.c_void_p(dW.data_ptr()), ctypes.c_void_p(dC.data_ptr()),
+                                                  int(time_steps), ctypes.c_void_p(d_logits.data_ptr()),
+                                                  ctypes.c_void_p(d_preds.data_ptr()), self._sptr(stream)))
+
+    def init_embeddings(self, dW, dC, stream=None):
+        _lib.check(_lib.lib.tspgnn_init_embeddings(self._h, ctypes.c_void_p(dW.data_ptr()),
+                                                   ctypes.c_void_p(dC.data_ptr()), self._sptr(stream)))
+
+    def step(self, n_steps, stream=None):
+        _lib.check(_lib.lib.tspgnn_step(self._h, int(n_steps), self._sptr(stream)))
+
+    def readout(self, d_logits, d_preds, stream=None):
+        _lib.check(_lib.lib.tspgnn_readout(self._h, ctypes.c_void_p(d_logits.data_ptr()),
+                                           ctypes.c_void_p(d_preds.data_ptr()), self._sptr(stream)))
+
+    def get_states(self, stream=None):
+        """{'V': (c,h), 'E': (c,h)} as row-major fp32 torch tensors on the device."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        s = stream if stream is not None else self.stream()
+        Vh = torch.empty(self.n_vertices_total, self.d, dtype=torch.float32, device=dev)
+        Vc = torch.empty_like(Vh)
+        Eh = torch.empty(self.n_edges_total, self.d, dtype=torch.float32, device=dev)
+        Ec = torch.empty_like(Eh)
+        _lib.check(_lib.lib.tspgnn_get_states(self._h, *[ctypes.c_void_p(t.data_ptr()) for t in (Vh, Vc, Eh, Ec)],
+                                              self._sptr(s)))
+        s.synchronize()
+        return {"V": (Vc, Vh), "E": (Ec, Eh)}
+
+    def set_states(self, Vh=None, Vc=None, Eh=None, Ec=None, stream=None):
+        s = stream if stream is not None else self.stream()
+        ptrs = [ctypes.c_void_p(t.data_ptr()) if t is not None else None for t in (Vh, Vc, Eh, Ec)]
+        _lib.check(_lib.lib.tspgnn_set_states(self._h, *ptrs, self._sptr(s)))
+        s.synchronize()
+
+    def time_kernel(self, which, iters, stream=None):
+        """Mean device time (ms) of one launch of K1 (which=0) or K2 (which=1)."""
+        ms = ctypes.c_float(0)
+        _lib.check(_lib.lib.tspgnn_time_kernel(self._h, int(which), int(iters), ctypes.byref(ms), self._sptr(stream)))
+        return float(ms.value)
+
+    @property
+    def launch_count(self):
+        return int(_lib.lib.tspgnn_launch_count(self._h))
+
+
+def dense_ev_to_coo(EV):
+    """Dense [sumE,sumV] float32/float64 EV -> (edge_src, edge_dst) via the C helper."""
+    EV = np.ascontiguousarray(EV)
+    if EV.dtype not in (np.float32, np.float64):
+        EV = EV.astype(np.float32)
+    src = np.empty(EV.shape[0], dtype=np.int32)
+    dst = np.empty(EV.shape[0], dtype=np.int32)
+    _lib.check(_lib.lib.tspgnn_dense_ev_to_coo(_np_ptr(EV), EV.dtype.itemsize, EV.shape[0], EV.shape[1],
+                                               _np_ptr(src), _np_ptr(dst)))
+    return src, dst

@@ -1,0 +1,214 @@
+"""``build_network(d)`` and a minimal ``Session`` so that train.py / test.py style drivers of
+the reference run unchanged against the CUDA engine (model.py:9-171, train.py:17-63).
+
+``build_network`` returns a dict with the reference's keys; the values are light handles
+(:class:`Placeholder`, :class:`Fetch`) that ``Session.run(fetches, feed_dict)`` resolves:
+
+    GNN = build_network(64)
+    with Session(GNN) as sess:
+        sess.run(global_variables_initializer())
+        loss, acc, predictions, TP, FP, TN, FN = sess.run(
+            [GNN['loss'], GNN['acc'], GNN['predictions'], GNN['TP'], GNN['FP'], GNN['TN'], GNN['FN']],
+            feed_dict={GNN['EV']: EV, GNN['W']: W, GNN['C']: C, GNN['time_steps']: 32,
+                       GNN['route_exists']: y, GNN['n_vertices']: nv, GNN['n_edges']: ne})
+
+``EV`` may be the reference's dense ``[sumE,sumV]`` array or an ``instances.Incidence``.
+``train_step`` is declared but raises: the backward pass is outside this round's scope.
+"""
+import numpy as np
+
+from .graphnn import GraphNN, LSTMStateTuple
+from .mlp import Mlp
+from .instances import Incidence
+from . import params as _params
+
+
+class Placeholder(object):
+    def __init__(self, name, dtype, shape):
+        self.name, self.dtype, self.shape = name, dtype, shape
+
+    def __repr__(self):
+        return "<Placeholder %s>" % self.name
+
+
+class Fetch(object):
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return "<Fetch %s>" % self.name
+
+
+class _InitOp(object):
+    def __init__(self, seed=None):
+        self.seed = seed
+
+
+def global_variables_initializer(seed=None):
+    """tf.global_variables_initializer() analogue (train.py:210): draws every trainable
+    variable from the reference's initialisers."""
+    return _InitOp(seed)
+
+
+def build_network(d, mode="bf16x3", device=0):
+    # hyper-parameters of model.py:13-15 (used by the training step, not built yet)
+    learning_rate = 2e-5
+    l2norm_scaling = 1e-10
+    global_norm_gradient_clipping_ratio = 0.65
+
+    route_exists = Placeholder("route_exists", np.float32, (None,))          # model.py:18
+    n_vertices = Placeholder("n_vertices", np.int32, (None,))                # model.py:20
+    n_edges = Placeholder("edges", np.int32, (None,))                        # model.py:21
+    EV_matrix = Placeholder("EV", np.float32, (None, None))                  # model.py:23
+    edge_weight = Placeholder("edge_weight", np.float32, (None, 1))          # model.py:25
+    target_cost = Placeholder("target_cost", np.float32, (None, 1))          # model.py:27
+    time_steps = Placeholder("time_steps", np.int32, ())                     # model.py:29
+
+    edge_init_MLP = Mlp(layer_sizes=[d / 8, d / 4, d / 2], activations=["relu" for _ in range(3)], output_size=d,
+                        name="E_init_MLP", name_internal_layers=True, kernel_initializer="xavier",
+                        bias_initializer="zeros")                           # model.py:33-41
+
+    gnn = GraphNN(
+        {"V": d, "E": d},
+        {"EV": ("E", "V")},
+        {"V_msg_E": ("V", "E"), "E_msg_V": ("E", "V")},
+        {
+            "V": [{"mat": "EV", "msg": "E_msg_V", "transpose?": True, "var": "E"}],   # V(t+1) <- Vu(EV^T x E_msg_V(E(t)))
+            "E": [{"mat": "EV", "msg": "V_msg_E", "var": "V"}],                       # E(t+1) <- Eu(EV x V_msg_E(V(t)))
+        },
+        name="TSP")                                                          # model.py:57-94
+
+    E_vote_MLP = Mlp(layer_sizes=[d for _ in range(3)], activations=["relu" for _ in range(3)], output_size=1,
+                     name="E_vote", name_internal_layers=True, kernel_initializer="xavier",
+                     bias_initializer="zeros")                              # model.py:107-115
+
+    GNN = {}
+    GNN["gnn"] = gnn
+    GNN["route_exists"] = route_exists
+    GNN["n_vertices"] = n_vertices
+    GNN["n_edges"] = n_edges
+    GNN["EV"] = EV_matrix
+    GNN["W"] = edge_weight
+    GNN["C"] = target_cost
+    GNN["time_steps"] = time_steps
+    GNN["last_states"] = Fetch("last_states")                               # model.py:123
+    for k in ("predictions", "TP", "FP", "TN", "FN", "acc", "loss", "train_step"):
+        GNN[k] = Fetch(k)                                                    # model.py:147-167
+    # not part of the reference dict: construction-time settings Session needs
+    GNN["_config"] = {"d": d, "mode": mode, "device": device, "E_init_MLP": edge_init_MLP, "E_vote_MLP": E_vote_MLP,
+                      "learning_rate": learning_rate, "l2norm_scaling": l2norm_scaling,
+                      "clip": global_norm_gradient_clipping_ratio}
+    return GNN
+
+
+def _metrics(logits, predictions, route_exists):
+    """model.py:150-157, evaluated on the host from the [B] logits the device returns."""
+    y = np.asarray(route_exists, dtype=np.float32)
+    l = logits.astype(np.float32)
+    r = np.round(predictions)
+    eq = (y == r).astype(np.float32)
+    ne = 1.0 - eq
+    xent = np.maximum(l, 0) - l * y + np.log1p(np.exp(-np.abs(l)))   # sigmoid_cross_entropy_with_logits
+    return {
+        "TP": np.float32((y * eq).sum()), "FP": np.float32((y * ne).sum()),       # model.py:150-151 (reference's naming)
+        "TN": np.float32(((1 - y) * eq).sum()), "FN": np.float32(((1 - y) * ne).sum()),
+        "acc": np.float32(eq.mean()), "loss": np.float32(xent.mean()),
+    }
+
+
+class Session(object):
+    """tf.Session stand-in bound to one GPU engine."""
+
+    def __init__(self, GNN=None, config=None):
+        self._gnn = GNN
+        self._engine = None
+        self._params = None
+        self._plan_key = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    # -- variables ----------------------------------------------------------------
+    def _ensure_engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            cfg = self._gnn["_config"]
+            self._engine = Engine(cfg["d"], cfg["mode"], cfg["device"])
+            self._gnn["gnn"].bind(self._engine)
+        return self._engine
+
+    def set_variables(self, params):
+        self._params = {k: np.asarray(v, dtype=np.float32) for k, v in params.items()}
+        self._ensure_engine().set_params(self._params)
+
+    def get_variables(self):
+        return dict(self._params)
+
+    def load_weights(self, path):
+        self.set_variables(_params.load_weights(path))
+
+    def save_weights(self, path):
+        _params.save_weights(self._params, path)
+
+    # -- run ------------------------------------------------------------------------
+    def run(self, fetches, feed_dict=None):
+        if self._gnn is None:
+            raise RuntimeError("Session was created without a network")
+        if isinstance(fetches, _InitOp):
+            self.set_variables(_params.init_params(self._gnn["_config"]["d"], seed=fetches.seed))
+            return None
+        single = not isinstance(fetches, (list, tuple))
+        flist = [fetches] if single else list(fetches)
+        feed = {}
+        for k, v in (feed_dict or {}).items():
+            feed[k.name if isinstance(k, Placeholder) else str(k)] = v
+        names = [f.name for f in flist]
+        if "train_step" in names:
+            raise NotImplementedError("train_step (backward pass + Adam, model.py:157-167) is not built yet")
+        if self._params is None:
+            raise RuntimeError("Attempting to use uninitialized variables: run global_variables_initializer() "
+                               "or load_weights() first")
+        for need in ("EV", "edge_weight", "target_cost", "time_steps", "n_vertices", "edges"):
+            if need not in feed:
+                raise ValueError("You must feed a value for placeholder %r" % need)
+        eng = self._ensure_engine()
+        EV = feed["EV"]
+        if not isinstance(EV, Incidence):
+            from .engine import dense_ev_to_coo
+            EVd = np.asarray(EV)
+            src, dst = dense_ev_to_coo(EVd)
+            EV = Incidence(src, dst, EVd.shape[1])
+        nv = np.asarray(feed["n_vertices"]).astype(np.int64)
+        ne = np.asarray(feed["edges"]).astype(np.int64)
+        W = np.asarray(feed["edge_weight"], dtype=np.float32).reshape(-1)
+        C = np.asarray(feed["target_cost"], dtype=np.float32).reshape(-1)
+        # shape checks of graphnn.check_run on the fed matrices
+        if EV.shape[0] != int(ne.sum()) or EV.shape[0] != W.shape[0] or W.shape != C.shape:
+            raise ValueError("Matrix EV doesn't have the same number of nodes as the initial embeddings of its variable E")
+        if EV.shape[1] != int(nv.sum()):
+            raise ValueError("Matrix EV doesn't have the same number of nodes as the initial embeddings of its variable V")
+        key = (EV.src.tobytes(), EV.dst.tobytes(), nv.tobytes(), ne.tobytes())
+        if key != self._plan_key:
+            eng.plan(nv, ne, EV.src, EV.dst)
+            self._plan_key = key
+        logits, preds = eng.forward_host(W, C, int(feed["time_steps"]))
+        out = {"predictions": preds, "logits": logits}
+        if any(n in names for n in ("TP", "FP", "TN", "FN", "acc", "loss")):
+            if "route_exists" not in feed:
+                raise ValueError("You must feed a value for placeholder 'route_exists'")
+            out.update(_metrics(logits, preds, feed["route_exists"]))
+        if "last_states" in names:
+            st = eng.get_states()
+            out["last_states"] = {v: LSTMStateTuple(c=st[v][0].cpu().numpy(), h=st[v][1].cpu().numpy())
+                                  for v in ("V", "E")}
+        res = [out[n] for n in names]
+        return res[0] if single else res
