@@ -160,6 +160,33 @@ def dense_EV(src, dst, n_vertices_total, dtype):
     return EV
 
 
+def message_passing(P, src, dst, EV, E_c, E_h, V_c, V_h, time_steps, trace=None):
+    """The hot loop: ``time_steps`` iterations of while_body (graphnn.py:142-173, driven by
+    tf.while_loop graphnn.py:175-179).  ``EV`` dense [sumE,sumV] multiplies exactly like
+    graphnn.py:156-160; ``EV=None`` uses the gather / segment-sum form of the same products.
+    ``P`` must already be cast to the working dtype.  Returns (E_c, E_h, V_c, V_h)."""
+    dtype = E_h.dtype
+    nV, d = V_h.shape
+    for _ in range(int(time_steps)):
+        mE = mlp(E_h, P, "TSP/E_msg_V")                     # graphnn.py:152-154
+        mV = mlp(V_h, P, "TSP/V_msg_E")
+        if EV is not None:
+            xV = EV.T @ mE                                   # graphnn.py:156-160, adjoint_a=True
+            xE = EV @ mV
+        else:
+            xV = np.zeros((nV, d), dtype=dtype)
+            np.add.at(xV, src, mE)
+            np.add.at(xV, dst, mE)
+            xE = mV[src] + mV[dst]
+        # both cells read the time-t states (graphnn.py:144-148)
+        nVc, nVh = lnlstm(xV, V_c, V_h, P, "TSP/V_cell/layer_norm_basic_lstm_cell")
+        nEc, nEh = lnlstm(xE, E_c, E_h, P, "TSP/E_cell/layer_norm_basic_lstm_cell")
+        V_c, V_h, E_c, E_h = nVc, nVh, nEc, nEh
+        if trace is not None:
+            trace.append(dict(mE=mE, mV=mV, xV=xV, xE=xE, V_c=V_c, V_h=V_h, E_c=E_c, E_h=E_h))
+    return E_c, E_h, V_c, V_h
+
+
 # ----------------------------------------------------------------------------
 # forward pass (SURVEY.md appendix B)
 # ----------------------------------------------------------------------------
@@ -190,24 +217,8 @@ def forward(params, src, dst, W, C, n_vertices, n_edges, time_steps,
     V_c = np.zeros_like(V_h)
 
     EV = dense_EV(src, dst, nV, dtype) if dense else None
-    trace = []
-    for _ in range(int(time_steps)):                         # graphnn.py:175-179
-        mE = mlp(E_h, P, "TSP/E_msg_V")                     # graphnn.py:152-154
-        mV = mlp(V_h, P, "TSP/V_msg_E")
-        if dense:
-            xV = EV.T @ mE                                   # graphnn.py:156-160, adjoint_a=True
-            xE = EV @ mV
-        else:
-            xV = np.zeros((nV, d), dtype=dtype)
-            np.add.at(xV, src, mE)
-            np.add.at(xV, dst, mE)
-            xE = mV[src] + mV[dst]
-        # both cells read the time-t states (graphnn.py:144-148)
-        nVc, nVh = lnlstm(xV, V_c, V_h, P, "TSP/V_cell/layer_norm_basic_lstm_cell")
-        nEc, nEh = lnlstm(xE, E_c, E_h, P, "TSP/E_cell/layer_norm_basic_lstm_cell")
-        V_c, V_h, E_c, E_h = nVc, nVh, nEc, nEh
-        if return_trace:
-            trace.append(dict(mE=mE, mV=mV, xV=xV, xE=xE, V_c=V_c, V_h=V_h, E_c=E_c, E_h=E_h))
+    trace = [] if return_trace else None
+    E_c, E_h, V_c, V_h = message_passing(P, src, dst, EV, E_c, E_h, V_c, V_h, time_steps, trace)
 
     E_vote = mlp(E_h, P, "E_vote").reshape(-1)               # model.py:124-128
     off = np.concatenate([[0], np.cumsum(n_edges)])

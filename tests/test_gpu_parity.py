@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the oracle.  Needs a B200.
 
-Tolerances (north star: outputs within 1e-4 of the fp32 reference path):
+Tolerances (north star: outputs within 1e-4 of the fp32 reference path).  Predictions are
+gated on absolute error; recurrent states on |got-ref| <= tol * max(1, |ref|) (LayerNorm'd
+cell states reach |c| ~ 4, so a pure absolute bound would be tighter than fp32-relative 1e-4):
   simt   fp32 FMA                       predictions 1e-5, states 1e-4
   bf16x3 tcgen05, hi/lo split operands  predictions 1e-4, states 1e-4
   bf16   tcgen05, bf16 embeddings       predictions 5e-3, states 1e-1 (BASELINE config 3:
@@ -24,6 +26,11 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_forward
 MODES = ["simt", "bf16x3", "bf16"]
 TOL_PRED = {"simt": 1e-5, "bf16x3": 1e-4, "bf16": 5e-3}
 TOL_STATE = {"simt": 1e-4, "bf16x3": 1e-4, "bf16": 1e-1}
+
+
+def state_err(got, ref):
+    """max over elements of |got-ref| / max(1, |ref|)."""
+    return float((np.abs(got - ref) / np.maximum(1.0, np.abs(ref))).max())
 
 
 def make_engine(mode, params):
@@ -52,13 +59,14 @@ def test_forward_matches_oracle_and_golden(mode, name):
     params = orc.init_params(64, seed=pseed, perturb_ln=perturb)
     got = run_engine(mode, params, EV, W, C, nv, ne, T)
     ref = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, T, dtype=np.float64)
-    err = {k: float(np.abs(got[k] - ref[k]).max()) for k in ("predictions", "E_h", "E_c", "V_h", "V_c")}
+    err = {k: state_err(got[k], ref[k]) for k in ("E_h", "E_c", "V_h", "V_c")}
+    err["predictions"] = float(np.abs(got["predictions"] - ref["predictions"]).max())
     print(mode, name, err)
     assert err["predictions"] <= TOL_PRED[mode], err
     for k in ("E_h", "E_c", "V_h", "V_c"):
         assert err[k] <= TOL_STATE[mode], err
     assert np.abs(got["predictions"] - GOLD[name + "/predictions"]).max() <= TOL_PRED[mode]
-    assert np.abs(got["E_c"][:32] - GOLD[name + "/E_c_head"]).max() <= TOL_STATE[mode]
+    assert state_err(got["E_c"][:32], GOLD[name + "/E_c_head"]) <= TOL_STATE[mode]
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -86,7 +94,7 @@ def test_single_timestep_from_random_state(mode):
     rEc, rEh = orc.lnlstm(xE, Ec.astype(np.float64), Eh.astype(np.float64), P64, "TSP/E_cell/layer_norm_basic_lstm_cell")
     tol = {"simt": 2e-5, "bf16x3": 5e-5, "bf16": 1e-1}[mode]
     for name, got, ref in (("V_c", st["V"][0], rVc), ("V_h", st["V"][1], rVh), ("E_c", st["E"][0], rEc), ("E_h", st["E"][1], rEh)):
-        err = float(np.abs(got.cpu().numpy() - ref).max())
+        err = state_err(got.cpu().numpy(), ref)
         print(mode, name, err)
         assert err <= tol, (name, err)
 
@@ -113,7 +121,7 @@ def test_full_size_north_star_config_matches_oracle(mode):
     got = run_engine(mode, params, EV, W, C, nv, ne, 32)
     ref = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, 32, dtype=np.float64)
     errp = float(np.abs(got["predictions"] - ref["predictions"]).max())
-    errs = float(np.abs(got["E_h"] - ref["E_h"]).max())
+    errs = state_err(got["E_h"], ref["E_h"])
     print(mode, "north-star pred err", errp, "E_h err", errs)
     assert errp <= TOL_PRED[mode] and errs <= TOL_STATE[mode]
 
