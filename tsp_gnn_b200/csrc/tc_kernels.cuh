@@ -1,39 +1,50 @@
 // Tensor-core (tcgen05) kernels of the message-passing timestep.
 //
 //   K1  tc_lnlstm_kernel : gather/segment input -> z = [x,h].K on tcgen05 (TMEM accumulator,
-//                          256 columns) -> 5x LayerNorm + gates in the epilogue -> new (c,h)
+//                          256 columns, double buffered) -> 5x LayerNorm + gates -> new (c,h)
 //                          (graphnn.py:155-170 for both variables of model.py:74-92)
 //   K2  tc_mlp_kernel    : 4-layer message MLP chained through TMEM (graphnn.py:152-154), then
 //                          E rows: scatter-add into xV (= EV^T . msg, model.py:76-83)
 //                          V rows: store the vertex message consumed by K1's gather
 //                          vote  : E_vote MLP, 64->1 tail in registers (model.py:107-128)
 //
-// HBM layout ("tile images"): recurrent state is stored per 128-row tile exactly as the
-// bytes the kernels want in shared memory, so one bulk async copy (UBLKCP) stages a tile:
-//   [h hi : 128 x 64 bf16, 128-B rows, 16-B chunks XOR-swizzled by (row & 7)]   16 KB
-//   [h lo : same, bf16(h - hi)]                      (HP == 2 only)            16 KB
-//   [c    : 128 x 64 fp32, 256-B rows, chunk ^= (row & 7)]                      32 KB
-// The h planes are directly the K-major SWIZZLE_128B UMMA A operand.  HP = number of bf16
-// planes: 2 -> every product is hi*hi + hi*lo + lo*hi (fp32-parity mode), 1 -> single bf16.
+// Both are persistent, warp-specialised CTAs of 384 threads (one per SM):
+//   warps 0-3, 4-7 : two epilogue warpgroups, one 128-row tile each (thread = row = TMEM lane)
+//   warp  8        : tcgen05.mma issuer (one lane), owns the TMEM allocation
+//   warps 9-11     : producers (K1: gather of the x operand + bulk copies of h; K2: bulk copies)
+//
+// HBM layout ("tile images"): the recurrent state of 128 consecutive rows is stored as
+//   [h hi : 8 chunks x 128 rows x 16 B (8 bf16)]   16 KB   chunk-major = un-swizzled K-major UMMA
+//   [h lo : same, bf16(h - hi)]  (HP == 2 only)    16 KB   canonical layout (LBO 2048, SBO 128)
+//   [c    : 16 chunks x 128 rows x 16 B (4 fp32)]  32 KB
+// so that (a) one bulk async copy (UBLKCP) stages the h planes as the MMA A operand and (b) the
+// epilogue threads (one row each) read c and write c', h' straight from / to global memory with
+// fully coalesced 16-byte accesses (a warp covers 512 contiguous bytes per instruction).
+// HP = number of bf16 planes: 2 -> every product is hi*hi + hi*lo + lo*hi (fp32-parity mode),
+// 1 -> single bf16.
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace tspgnn {
 
-constexpr int IMG16_BYTES = TILE_ROWS * 128;   // one bf16 plane of a tile
-constexpr int IMG32_BYTES = TILE_ROWS * 256;   // fp32 tile
-constexpr int STAGE_LD = 66;                   // fp32 staging row stride (floats)
-constexpr int STAGE_BYTES = 34 * 1024;         // >= 128*66*4
+constexpr int PLANE_BYTES = TILE_ROWS * 128;   // one bf16 plane of a tile
+constexpr int CT_BYTES = TILE_ROWS * 256;      // fp32 c tile
+constexpr int TC_THREADS = 384;
+constexpr int NUM_GATHER_WARPS = 3;
 
-__host__ __device__ constexpr int tile_bytes(int hp) { return hp * IMG16_BYTES + IMG32_BYTES; }
+__host__ __device__ constexpr int tile_bytes(int hp) { return hp * PLANE_BYTES + CT_BYTES; }
 
-// byte offset of element (row, col) inside a bf16 plane / fp32 tile image
-__host__ __device__ inline uint32_t img16_off(int r, int col) {
-  return static_cast<uint32_t>(r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2);
+// byte offset of element (row, col) inside a bf16 plane / the fp32 c tile
+__host__ __device__ inline uint32_t plane_off(int r, int col) {
+  return static_cast<uint32_t>((col >> 3) * 2048 + r * 16 + (col & 7) * 2);
 }
-__host__ __device__ inline uint32_t img32_off(int r, int col) {
-  return static_cast<uint32_t>(r * 256 + (((col >> 2) ^ (r & 7)) << 4) + (col & 3) * 4);
+__host__ __device__ inline uint32_t ct_off(int r, int col) {
+  return static_cast<uint32_t>((col >> 2) * 2048 + r * 16 + (col & 3) * 4);
+}
+// B operand image of n_rows output features x 64 k-values (bf16), same chunk-major layout
+__host__ __device__ inline uint32_t wimg_off(int n, int k, int n_rows) {
+  return static_cast<uint32_t>((k >> 3) * (n_rows * 16) + n * 16 + (k & 7) * 2);
 }
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -50,7 +61,7 @@ struct K1Args {
   const uint8_t* wV;
   const float* mV;     // vertex messages [sumV][64] (E rows gather two of them)
   float* xV;           // summed edge messages [sumV_pad][64]; V rows read and then zero it
-  const int32_t* src;
+  const int32_t* src;  // [sumE_pad], zero padded
   const int32_t* dst;
   int64_t nE, nV;
   int tilesE, tilesV, e_ctas;
@@ -77,149 +88,200 @@ __device__ __forceinline__ void tile_range(int i, int n, int tiles, int& t0, int
   t1 = static_cast<int>((static_cast<int64_t>(i + 1) * tiles) / n);
 }
 
+// 8 fp32 -> one 16-byte chunk of bf16 hi (+ one of bf16 lo)
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  ptx::split_bf16x2(x[0], x[1], hi.x, lo.x);
+  ptx::split_bf16x2(x[2], x[3], hi.y, lo.y);
+  ptx::split_bf16x2(x[4], x[5], hi.z, lo.z);
+  ptx::split_bf16x2(x[6], x[7], hi.w, lo.w);
+}
+
 // ====================================================================================
 // K1: LayerNorm-LSTM step
 // ====================================================================================
 template <int HP>
 struct K1Smem {
   static constexpr int W_BYTES = HP * 2 * 256 * 128;       // [plane][kblock] 32 KB images
-  static constexpr int X_OFF = W_BYTES;                    // x planes   (A operand, k-block 0)
-  static constexpr int H_OFF = X_OFF + HP * IMG16_BYTES;   // h planes   (A operand, k-block 1)
-  static constexpr int C_OFF = H_OFF + HP * IMG16_BYTES;   // c tile (contiguous after h: one tile image)
-  static constexpr int BAR_OFF = C_OFF + IMG32_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 64;
-  static constexpr int DYN_BYTES = TOTAL + 1024;           // slack for 1024-B alignment
+  static constexpr int SLOT_BYTES = HP * PLANE_BYTES;      // all planes of one A k-block (x or h)
+  static constexpr int NSLOT = (HP == 2) ? 3 : 6;          // ring of operand slots: x(t), h(t), x(t+1), ...
+  static constexpr int RING_OFF = W_BYTES;
+  static constexpr int BAR_OFF = RING_OFF + NSLOT * SLOT_BYTES;
+  static constexpr int NBAR = 1 + 2 * NSLOT + 4;
+  static constexpr int TOTAL = BAR_OFF + 8 * NBAR + 16;
+  static constexpr int DYN_BYTES = TOTAL + 128;            // slack for 128-B alignment
 };
 
-template <int HP>
-__global__ void __launch_bounds__(128, 1) tc_lnlstm_kernel(const K1Args a) {
-  using L = K1Smem<HP>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* wsm = smem;
-  uint8_t* xbuf = smem + L::X_OFF;
-  uint8_t* hbuf = smem + L::H_OFF;
-  uint8_t* cbuf = smem + L::C_OFF;
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* bar_ld = bar_w + 1;
-  uint64_t* bar_mma = bar_w + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
-  const int cell = is_v ? 0 : 1;
-  int t0, t1;
-  if (is_v) tile_range(blockIdx.x - a.e_ctas, gridDim.x - a.e_ctas, a.tilesV, t0, t1);
-  else tile_range(blockIdx.x, a.e_ctas, a.tilesE, t0, t1);
-  uint8_t* state = is_v ? a.stateV : a.stateE;
-  const int64_t n_rows = is_v ? a.nV : a.nE;
-
-  if (tid == 0) {
-    ptx::mbar_init(bar_w, 1);
-    ptx::mbar_init(bar_ld, 1);
-    ptx::mbar_init(bar_mma, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
-  ptx::tcgen05_fence_before();
-  __syncthreads();
-  ptx::tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (tid == 0 && t0 < t1) {
-    const uint8_t* wimg = is_v ? a.wV : a.wE;
-    ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-    for (int off = 0; off < L::W_BYTES; off += 32768) ptx::bulk_g2s(wsm + off, wimg + off, 32768, bar_w);
-  }
-
-  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 256);
-  const CellLN& ln = c_ln[cell];
-  const int r = tid;                                  // row of the tile owned in the epilogue
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  uint32_t phase = 0;
-
-  for (int tile = t0; tile < t1; ++tile) {
-    uint8_t* gtile = state + static_cast<int64_t>(tile) * tile_bytes(HP);
-    const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
-    // ---- stage h planes + c: one contiguous tile image ------------------------------
-    if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(bar_ld, tile_bytes(HP));
-      ptx::bulk_g2s(hbuf, gtile, tile_bytes(HP), bar_ld);
-    }
-    // ---- build x planes: E rows x = mV[src]+mV[dst] (= EV.msg), V rows x = xV (then cleared)
-    {
-      int64_t grow = row0 + warp * 32 + lane;
-      int my_s = 0, my_d = 0;
-      if (!is_v && grow < n_rows) {
-        my_s = a.src[grow];
-        my_d = a.dst[grow];
-      }
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const int row = warp * 32 + rr;
-        const int64_t g = row0 + row;
-        float2 x = make_float2(0.f, 0.f);
-        if (is_v) {
-          if (g < n_rows) {
-            float2* p = reinterpret_cast<float2*>(a.xV + g * D) + lane;
-            x = *p;
-            *p = make_float2(0.f, 0.f);
-          }
+// ---- producer: build the x operand of one tile in shared memory ------------------------
+// E rows: x = mV[src] + mV[dst] (= EV . msg, model.py:85-91); V rows: x = xV (then cleared).
+// A warp instruction covers 8 rows x 4 chunks: lane -> (row r8 = lane & 7, chunk cq = lane >> 3),
+// so every quarter-warp writes 128 contiguous bytes of shared memory (no bank conflicts).
+template <int HP, bool IS_V>
+__device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64_t row0, const float* __restrict__ mV,
+                                          float* __restrict__ xV, const int (&si)[6], const int (&di)[6]) {
+  const int r8 = lane & 7, cq = lane >> 3;
+#pragma unroll
+  for (int gi = 0; gi < 6; ++gi) {
+    const int g = gw + NUM_GATHER_WARPS * gi;
+    if (g < 16) {
+      const int row = g * 8 + r8;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int chunk = cq + 4 * j;
+        float x[8];
+        if (IS_V) {
+          float4* p = reinterpret_cast<float4*>(xV + (row0 + row) * D + chunk * 8);
+          const float4 u0 = p[0], u1 = p[1];
+          p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
+          x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
         } else {
-          const int s = __shfl_sync(0xffffffffu, my_s, rr);
-          const int d = __shfl_sync(0xffffffffu, my_d, rr);
-          if (g < n_rows) {
-            const float2 u = __ldg(reinterpret_cast<const float2*>(a.mV + static_cast<int64_t>(s) * D) + lane);
-            const float2 w = __ldg(reinterpret_cast<const float2*>(a.mV + static_cast<int64_t>(d) * D) + lane);
-            x = make_float2(u.x + w.x, u.y + w.y);
-          }
+          const float4* ps = reinterpret_cast<const float4*>(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8);
+          const float4* pd = reinterpret_cast<const float4*>(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8);
+          const float4 u0 = __ldg(ps), u1 = __ldg(ps + 1), w0 = __ldg(pd), w1 = __ldg(pd + 1);
+          x[0] = u0.x + w0.x; x[1] = u0.y + w0.y; x[2] = u0.z + w0.z; x[3] = u0.w + w0.w;
+          x[4] = u1.x + w1.x; x[5] = u1.y + w1.y; x[6] = u1.z + w1.z; x[7] = u1.w + w1.w;
         }
-        uint32_t hi, lo;
-        ptx::split_bf16x2(x.x, x.y, hi, lo);
-        const uint32_t off = img16_off(row, 2 * lane);
-        *reinterpret_cast<uint32_t*>(xbuf + off) = hi;
-        if (HP == 2) *reinterpret_cast<uint32_t*>(xbuf + IMG16_BYTES + off) = lo;
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = chunk * 2048 + row * 16;
+        *reinterpret_cast<uint4*>(slot + off) = hi;
+        if (HP == 2) *reinterpret_cast<uint4*>(slot + PLANE_BYTES + off) = lo;
       }
     }
-    ptx::fence_proxy_async_smem();
-    __syncthreads();
-    // ---- MMA: z[128 x 256] = [x,h] . K ------------------------------------------------
-    if (tid == 0) {
-      if (tile == t0) ptx::mbar_wait(bar_w, 0);
-      ptx::mbar_wait(bar_ld, phase);
+  }
+}
+
+template <int HP, bool IS_V>
+__device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uint8_t* ring, uint64_t* full,
+                                            uint64_t* empty, int t0, int ntiles, int gw, int lane) {
+  using L = K1Smem<HP>;
+  const int r8 = lane & 7;
+  int si[6], di[6];
+#pragma unroll
+  for (int gi = 0; gi < 6; ++gi) si[gi] = di[gi] = 0;
+  auto load_idx = [&](int tile, int (&s)[6], int (&d)[6]) {
+    if (IS_V) return;
+    const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
+#pragma unroll
+    for (int gi = 0; gi < 6; ++gi) {
+      const int g = gw + NUM_GATHER_WARPS * gi;
+      if (g < 16) {
+        s[gi] = __ldg(a.src + row0 + g * 8 + r8);
+        d[gi] = __ldg(a.dst + row0 + g * 8 + r8);
+      }
+    }
+  };
+  load_idx(t0, si, di);
+  for (int n = 0; n < ntiles; ++n) {
+    const int tile = t0 + n;
+    // ---- x operand (k-block 0) ---------------------------------------------------------
+    {
+      const int seq = 2 * n, slot = seq % L::NSLOT, use = seq / L::NSLOT;
+      int sn[6], dn[6];
+#pragma unroll
+      for (int gi = 0; gi < 6; ++gi) sn[gi] = dn[gi] = 0;
+      if (n + 1 < ntiles) load_idx(tile + 1, sn, dn);     // next tile's column indices, a tile ahead
+      if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
+      k1_fill_x<HP, IS_V>(ring + slot * L::SLOT_BYTES, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, a.mV, a.xV,
+                          si, di);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full[slot]);
+#pragma unroll
+      for (int gi = 0; gi < 6; ++gi) {
+        si[gi] = sn[gi];
+        di[gi] = dn[gi];
+      }
+    }
+    // ---- h operand (k-block 1): the h planes of the tile image, one bulk copy ------------
+    {
+      const int seq = 2 * n + 1, slot = seq % L::NSLOT, use = seq / L::NSLOT;
+      if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
+      if (lane == 0) {
+        if (gw == 0) {
+          ptx::mbar_arrive_expect_tx(&full[slot], L::SLOT_BYTES);
+          ptx::bulk_g2s(ring + slot * L::SLOT_BYTES, state + static_cast<int64_t>(tile) * tile_bytes(HP),
+                        L::SLOT_BYTES, &full[slot]);
+        } else {
+          ptx::mbar_arrive(&full[slot]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- MMA issuer: z[128 x 256] = [x,h] . K, accumulators alternate between two TMEM halves ----
+template <int HP>
+__device__ __forceinline__ void k1_mma(const uint8_t* wimg, uint8_t* wsm, uint8_t* ring, uint64_t* bar_w,
+                                       uint64_t* full, uint64_t* empty, uint64_t* acc_full, uint64_t* acc_empty,
+                                       uint32_t tmem, int ntiles) {
+  using L = K1Smem<HP>;
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 256);
+  ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+  for (int off = 0; off < L::W_BYTES; off += 32768) ptx::bulk_g2s(wsm + off, wimg + off, 32768, bar_w);
+  ptx::mbar_wait(bar_w, 0);
+  for (int n = 0; n < ntiles; ++n) {
+    const int acc = n & 1, k_use = n >> 1;
+    if (k_use >= 1) ptx::mbar_wait(&acc_empty[acc], (k_use - 1) & 1);
+    ptx::tcgen05_fence_after();
+    const uint32_t d_tmem = tmem + acc * 256;
+    uint32_t accumulate = 0;
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      const int seq = 2 * n + kb, slot = seq % L::NSLOT, use = seq / L::NSLOT;
+      ptx::mbar_wait(&full[slot], use & 1);
       ptx::tcgen05_fence_after();
-      uint32_t acc = 0;
       // (A plane, B plane): small cross terms first, then hi*hi
       constexpr int NCOMB = (HP == 2) ? 3 : 1;
       const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
 #pragma unroll
       for (int cb = 0; cb < NCOMB; ++cb) {
         const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
+        const uint32_t abase = ptx::smem_u32(ring + slot * L::SLOT_BYTES + pa * PLANE_BYTES);
+        const uint32_t bbase = ptx::smem_u32(wsm + (pb * 2 + kb) * 32768);
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint32_t abase = ptx::smem_u32((kb == 0 ? xbuf : hbuf) + pa * IMG16_BYTES);
-          const uint32_t bbase = ptx::smem_u32(wsm + (pb * 2 + kb) * 32768);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ptx::umma_bf16_ss(tmem, ptx::umma_desc_k_sw128(abase + k * 32), ptx::umma_desc_k_sw128(bbase + k * 32),
-                              IDESC, acc);
-            acc = 1;
-          }
+        for (int k = 0; k < 4; ++k) {
+          ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_k_nosw(abase + k * 4096, 2048, 128),
+                            ptx::umma_desc_k_nosw(bbase + k * 8192, 4096, 128), IDESC, accumulate);
+          accumulate = 1;
         }
       }
-      ptx::umma_commit(bar_mma);
+      ptx::umma_commit(&empty[slot]);
     }
-    __syncwarp();
-    ptx::mbar_wait(bar_ld, phase);     // c tile visible to every thread
-    ptx::mbar_wait(bar_mma, phase);
+    ptx::umma_commit(&acc_full[acc]);
+  }
+}
+
+// ---- epilogue: thread r owns row r (TMEM lane r) of the tiles of its warpgroup -----------
+template <int HP, int CELL>
+__device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
+                                            uint64_t* acc_empty, int warp, int lane) {
+  const int e = warp >> 2, q4 = warp & 3;
+  const int r = q4 * 32 + lane;
+  const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 256;
+  const CellLN& ln = c_ln[CELL];
+  int use = 0;
+  for (int n = e; n < ntiles; n += 2, ++use) {
+    uint8_t* gtile = state + static_cast<int64_t>(t0 + n) * tile_bytes(HP);
+    float4* cg = reinterpret_cast<float4*>(gtile + HP * PLANE_BYTES) + r;   // chunk q at cg[q * 128]
+    uint4* hg = reinterpret_cast<uint4*>(gtile) + r;                        // plane p, chunk ch at hg[p*1024 + ch*128]
+    // old cell state: issued before the accumulator is ready so the latency hides behind the MMA
+    float cn[64];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float4 t = cg[q * 128];
+      cn[4 * q] = t.x; cn[4 * q + 1] = t.y; cn[4 * q + 2] = t.z; cn[4 * q + 3] = t.w;
+    }
+    ptx::mbar_wait(&acc_full[e], use & 1);
     ptx::tcgen05_fence_after();
 
-    // ---- epilogue: thread r owns row r (TMEM lane r) ---------------------------------
     float mu[4], rs[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float v[64];
-      ptx::tmem_ld64(t_lane + g * 64, v);
+      ptx::tmem_ld64(t_acc + g * 64, v);
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; ++j) s += v[j];
@@ -230,29 +292,21 @@ __global__ void __launch_bounds__(128, 1) tc_lnlstm_kernel(const K1Args a) {
         const float t = v[j] - m;
         q = fmaf(t, t, q);
       }
-      mu[g] = m;
-      rs[g] = rsqrtf(q * (1.0f / 64) + LN_EPS);
+      const float rstd = rsqrtf(q * (1.0f / 64) + LN_EPS);
+      rs[g] = rstd;
+      mu[g] = -m * rstd;          // (v - m) * rstd = fma(v, rstd, -m * rstd)
     }
-    float cn[64];
-    uint8_t* crow = cbuf + r * 256;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-      float vi[16], vj[16], vf[16], cv[16];
-      ptx::tmem_ld16(t_lane + 0 * 64 + cc * 16, vi);
-      ptx::tmem_ld16(t_lane + 1 * 64 + cc * 16, vj);
-      ptx::tmem_ld16(t_lane + 2 * 64 + cc * 16, vf);
+      float vi[16], vj[16], vf[16];
+      ptx::tmem_ld16x3(t_acc + 0 * 64 + cc * 16, t_acc + 1 * 64 + cc * 16, t_acc + 2 * 64 + cc * 16, vi, vj, vf);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 t = *reinterpret_cast<const float4*>(crow + (((cc * 4 + q) ^ (r & 7)) << 4));
-        cv[q * 4 + 0] = t.x; cv[q * 4 + 1] = t.y; cv[q * 4 + 2] = t.z; cv[q * 4 + 3] = t.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = cc * 16 + e;
-        const float in = fmaf((vi[e] - mu[0]) * rs[0], ln.gamma[0][j], ln.beta[0][j]);
-        const float jn = fmaf((vj[e] - mu[1]) * rs[1], ln.gamma[1][j], ln.beta[1][j]);
-        const float fn = fmaf((vf[e] - mu[2]) * rs[2], ln.gamma[2][j], ln.beta[2][j]) + FORGET_BIAS;
-        cn[j] = fmaf(cv[e], fast_sigmoid(fn), fast_sigmoid(in) * fmaxf(jn, 0.f));
+      for (int el = 0; el < 16; ++el) {
+        const int j = cc * 16 + el;
+        const float in = fmaf(fmaf(vi[el], rs[0], mu[0]), ln.gamma[0][j], ln.beta[0][j]);
+        const float jn = fmaf(fmaf(vj[el], rs[1], mu[1]), ln.gamma[1][j], ln.beta[1][j]);
+        const float fn = fmaf(fmaf(vf[el], rs[2], mu[2]), ln.gamma[2][j], ln.beta[2][j]) + FORGET_BIAS;
+        cn[j] = fmaf(cn[j], fast_sigmoid(fn), fast_sigmoid(in) * fmaxf(jn, 0.f));
       }
     }
     float cm, crs;
@@ -260,59 +314,109 @@ __global__ void __launch_bounds__(128, 1) tc_lnlstm_kernel(const K1Args a) {
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; ++j) s += cn[j];
-      cm = s * (1.0f / 64);
+      const float m = s * (1.0f / 64);
       float q = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
-        const float t = cn[j] - cm;
+        const float t = cn[j] - m;
         q = fmaf(t, t, q);
       }
       crs = rsqrtf(q * (1.0f / 64) + LN_EPS);
+      cm = -m * crs;
     }
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       float vo[16], hn[16];
-      ptx::tmem_ld16(t_lane + 3 * 64 + cc * 16, vo);
+      ptx::tmem_ld16(t_acc + 3 * 64 + cc * 16, vo);
+      if (cc == 3) {     // last TMEM read of this tile: hand the accumulator back to the MMA warp
+        ptx::tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[e]);
+      }
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = cc * 16 + e;
-        const float on = fmaf((vo[e] - mu[3]) * rs[3], ln.gamma[3][j], ln.beta[3][j]);
-        const float c2 = fmaf((cn[j] - cm) * crs, ln.gamma[4][j], ln.beta[4][j]);
+      for (int el = 0; el < 16; ++el) {
+        const int j = cc * 16 + el;
+        const float on = fmaf(fmaf(vo[el], rs[3], mu[3]), ln.gamma[3][j], ln.beta[3][j]);
+        const float c2 = fmaf(fmaf(cn[j], crs, cm), ln.gamma[4][j], ln.beta[4][j]);
         cn[j] = c2;
-        hn[e] = fmaxf(c2, 0.f) * fast_sigmoid(on);
+        hn[el] = fmaxf(c2, 0.f) * fast_sigmoid(on);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int j = cc * 16 + q * 4;
-        *reinterpret_cast<float4*>(crow + (((cc * 4 + q) ^ (r & 7)) << 4)) =
-            make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]);
+        cg[(cc * 4 + q) * 128] = make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]);
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {   // two 16-B chunks of 8 bf16
-        uint32_t hi[4], lo[4];
+        float x[8];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) ptx::split_bf16x2(hn[q * 8 + 2 * p], hn[q * 8 + 2 * p + 1], hi[p], lo[p]);
-        const uint32_t off = r * 128 + (((cc * 2 + q) ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(hbuf + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (HP == 2) *reinterpret_cast<uint4*>(hbuf + IMG16_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int p = 0; p < 8; ++p) x[p] = hn[q * 8 + p];
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        hg[(cc * 2 + q) * 128] = hi;
+        if (HP == 2) hg[1024 + (cc * 2 + q) * 128] = lo;
       }
     }
-    // ---- write the tile image back in place --------------------------------------------
-    ptx::fence_proxy_async_smem();
-    ptx::tcgen05_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      ptx::bulk_s2g(gtile, hbuf, tile_bytes(HP));
-      ptx::bulk_commit();
-      ptx::bulk_wait_read0();
-    }
-    __syncthreads();
-    phase ^= 1;
   }
-  if (tid == 0) ptx::bulk_wait0();   // all tile images have landed in global memory
+}
+
+template <int HP>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a) {
+  using L = K1Smem<HP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* wsm = smem;
+  uint8_t* ring = smem + L::RING_OFF;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* full = bar_w + 1;
+  uint64_t* empty = full + L::NSLOT;
+  uint64_t* acc_full = empty + L::NSLOT;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
+  int t0, t1;
+  if (is_v) tile_range(blockIdx.x - a.e_ctas, gridDim.x - a.e_ctas, a.tilesV, t0, t1);
+  else tile_range(blockIdx.x, a.e_ctas, a.tilesE, t0, t1);
+  uint8_t* state = is_v ? a.stateV : a.stateE;
+  const int ntiles = t1 - t0;
+
+  if (tid == 0) {
+    ptx::mbar_init(bar_w, 1);
+    for (int s = 0; s < L::NSLOT; ++s) {
+      ptx::mbar_init(&full[s], NUM_GATHER_WARPS);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&acc_empty[s], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
   ptx::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    ptx::setmaxnreg_inc<200>();   // ... 256 x (200 - 168) = 8192 taken by the two epilogue warpgroups
+    if (is_v) k1_epilogue<HP, 0>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane);
+    else k1_epilogue<HP, 1>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane);
+  } else {
+    ptx::setmaxnreg_dec<104>();   // 128 x (168 - 104) = 8192 registers back to the CTA pool ...
+    if (warp == 8) {
+      if (lane == 0 && ntiles > 0)
+        k1_mma<HP>(is_v ? a.wV : a.wE, wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles);
+    } else {
+      if (is_v) k1_producer<HP, true>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
+      else k1_producer<HP, false>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc(tmem, 512);
 }
 
 // ====================================================================================
@@ -321,179 +425,237 @@ __global__ void __launch_bounds__(128, 1) tc_lnlstm_kernel(const K1Args a) {
 template <int HP>
 struct K2Smem {
   static constexpr int W_BYTES = 4 * HP * 8192;            // [layer][plane] 8 KB images
-  static constexpr int A_OFF = W_BYTES;
-  static constexpr int B_OFF = A_OFF + HP * IMG16_BYTES;
-  static constexpr int S_OFF = B_OFF + HP * IMG16_BYTES;   // fp32 staging for the scatter
-  static constexpr int BAR_OFF = S_OFF + STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 64;
-  static constexpr int DYN_BYTES = TOTAL + 1024;
+  static constexpr int IN_BYTES = HP * PLANE_BYTES;        // h planes of one tile
+  static constexpr int NIN = 3;                            // input slots (tile n -> slot n % 3)
+  static constexpr int P_BYTES = 32768;                    // per-warpgroup pong buffer; also the fp32 message staging
+  static constexpr int IN_OFF = W_BYTES;
+  static constexpr int P_OFF = IN_OFF + NIN * IN_BYTES;
+  static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;
+  static constexpr int NBAR = 1 + 2 * NIN + 4;
+  static constexpr int TOTAL = BAR_OFF + 8 * NBAR + 16;
+  static constexpr int DYN_BYTES = TOTAL + 128;
 };
 
-template <int HP>
-__global__ void __launch_bounds__(128, 1) tc_mlp_kernel(const K2Args a) {
+// fp32 staging of a 128 x 64 message tile: 256-B rows, 16-B chunk index XOR (row & 7)
+__device__ __forceinline__ uint32_t stage_off(int r, int chunk) {
+  return static_cast<uint32_t>(r * 256 + ((chunk ^ (r & 7)) << 4));
+}
+
+// ---- one warpgroup: epilogues of the layer chain of its tiles ------------------------------
+// ROLE 0 = V rows (V_msg_E, message stored), 1 = E rows (E_msg_V, scatter-add), 2 = E rows vote
+template <int HP, int ROLE>
+__device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint8_t* pbuf, uint64_t* acc_full,
+                                         uint64_t* act_ready, uint32_t tmem, int t0, int ntiles, int warp, int lane) {
   using L = K2Smem<HP>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* wsm = smem;
-  uint8_t* bufs[2] = {smem + L::A_OFF, smem + L::B_OFF};
-  float* stage = reinterpret_cast<float*>(smem + L::S_OFF);
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* bar_ld = bar_w + 1;
-  uint64_t* bar_mma = bar_w + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 3);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
-  const int bias_set = a.vote_mode ? 2 : (is_v ? 0 : 1);
-  int t0, t1;
-  if (is_v) tile_range(blockIdx.x - a.e_ctas, gridDim.x - a.e_ctas, a.tilesV, t0, t1);
-  else tile_range(blockIdx.x, a.e_ctas, a.tilesE, t0, t1);
-  const uint8_t* state = is_v ? a.stateV : a.stateE;
-  const int64_t n_rows = is_v ? a.nV : a.nE;
-  const int n_layers = a.vote_mode ? 3 : 4;
-
-  if (tid == 0) {
-    ptx::mbar_init(bar_w, 1);
-    ptx::mbar_init(bar_ld, 1);
-    ptx::mbar_init(bar_mma, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 0) ptx::tmem_alloc(tmem_slot, 64);
-  ptx::tcgen05_fence_before();
-  __syncthreads();
-  ptx::tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (tid == 0 && t0 < t1) {
-    const uint8_t* wimg = is_v ? a.wV : a.wE;
-    ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-    for (int off = 0; off < L::W_BYTES; off += 16384) ptx::bulk_g2s(wsm + off, wimg + off, 16384, bar_w);
-  }
-
-  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 64);
-  const MlpBias& bias = c_mlp_bias[bias_set];
-  const int r = tid;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  uint32_t ld_phase = 0, mma_phase = 0;
-
-  for (int tile = t0; tile < t1; ++tile) {
-    const uint8_t* gtile = state + static_cast<int64_t>(tile) * tile_bytes(HP);
-    const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
-    if (tid == 0) {
-      ptx::mbar_arrive_expect_tx(bar_ld, HP * IMG16_BYTES);
-      ptx::bulk_g2s(bufs[0], gtile, HP * IMG16_BYTES, bar_ld);
-    }
-    int cur = 0;
+  constexpr int NL = (ROLE == 2) ? 3 : 4;
+  const int e = warp >> 2, q4 = warp & 3;
+  const int r = q4 * 32 + lane;
+  const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 64;
+  const MlpBias& bias = c_mlp_bias[ROLE == 2 ? 2 : ROLE];
+  const int64_t n_rows = (ROLE == 0) ? a.nV : a.nE;
+  uint32_t step = 0;
+  for (int n = e; n < ntiles; n += 2) {
+    const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
+    uint8_t* ibuf = in_bufs + (n % L::NIN) * L::IN_BYTES;
     float v[64];
-    for (int l = 0; l < n_layers; ++l) {
-      if (tid == 0) {
-        if (l == 0) {
-          if (tile == t0) ptx::mbar_wait(bar_w, 0);
-          ptx::mbar_wait(bar_ld, ld_phase);
-        }
-        ptx::tcgen05_fence_after();
-        uint32_t acc = 0;
-        constexpr int NCOMB = (HP == 2) ? 3 : 1;
-        const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
 #pragma unroll
-        for (int cb = 0; cb < NCOMB; ++cb) {
-          const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
-          const uint32_t abase = ptx::smem_u32(bufs[cur] + pa * IMG16_BYTES);
-          const uint32_t bbase = ptx::smem_u32(wsm + (l * HP + pb) * 8192);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ptx::umma_bf16_ss(tmem, ptx::umma_desc_k_sw128(abase + k * 32), ptx::umma_desc_k_sw128(bbase + k * 32),
-                              IDESC, acc);
-            acc = 1;
-          }
-        }
-        ptx::umma_commit(bar_mma);
-      }
-      __syncwarp();
-      ptx::mbar_wait(bar_mma, mma_phase);
-      mma_phase ^= 1;
+    for (int l = 0; l < NL; ++l, ++step) {
+      ptx::mbar_wait(&acc_full[e], step & 1);
       ptx::tcgen05_fence_after();
-      ptx::tmem_ld64(t_lane, v);
-      const bool hidden = a.vote_mode || (l < 3);
+      ptx::tmem_ld64(t_acc, v);
+      const bool hidden = (ROLE == 2) || (l < 3);
+      const bool feeds_mma = l < NL - 1;
       if (hidden) {
-        uint8_t* nxt = bufs[cur ^ 1];
+        uint8_t* nxt = (l & 1) ? ibuf : pbuf;     // layer l reads (l even ? in : pong), writes the other
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-          uint32_t hi[4], lo[4];
+          float x[8];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int j = ch * 8 + 2 * p;
-            const float x0 = fmaxf(v[j] + bias.b[l][j], 0.f);
-            const float x1 = fmaxf(v[j + 1] + bias.b[l][j + 1], 0.f);
-            v[j] = x0;
-            v[j + 1] = x1;
-            ptx::split_bf16x2(x0, x1, hi[p], lo[p]);
+          for (int p = 0; p < 8; ++p) {
+            const int j = ch * 8 + p;
+            x[p] = fmaxf(v[j] + bias.b[l][j], 0.f);
+            v[j] = x[p];
           }
-          const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(nxt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (HP == 2) *reinterpret_cast<uint4*>(nxt + IMG16_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          if (feeds_mma) {
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const uint32_t off = ch * 2048 + r * 16;
+            *reinterpret_cast<uint4*>(nxt + off) = hi;
+            if (HP == 2) *reinterpret_cast<uint4*>(nxt + PLANE_BYTES + off) = lo;
+          }
         }
-        ptx::fence_proxy_async_smem();
-        cur ^= 1;
+        if (feeds_mma) ptx::fence_proxy_async_smem();
       }
       ptx::tcgen05_fence_before();
-      __syncthreads();
+      ptx::mbar_arrive(&act_ready[e]);            // activations written / accumulator drained
     }
-    ld_phase ^= 1;
     const int64_t grow = row0 + r;
-    if (a.vote_mode) {
+    if (ROLE == 2) {
       // 64 -> 1 tail of E_vote on the fp32 layer-3 activations (model.py:107-128)
       float s = c_vote_tail.b4;
 #pragma unroll
       for (int j = 0; j < 64; ++j) s = fmaf(v[j], c_vote_tail.w4[j], s);
       if (grow < n_rows) a.vote[grow] = s;
-    } else if (is_v) {
-      if (grow < n_rows) {
-        float4* out = reinterpret_cast<float4*>(a.mV + grow * D);
-#pragma unroll
-        for (int q = 0; q < 16; ++q)
-          out[q] = make_float4(v[4 * q] + bias.b[3][4 * q], v[4 * q + 1] + bias.b[3][4 * q + 1],
-                               v[4 * q + 2] + bias.b[3][4 * q + 2], v[4 * q + 3] + bias.b[3][4 * q + 3]);
-      }
     } else {
-      // stage messages, then each warp walks its 32 rows: dst side one vector reduction per
-      // row, src side accumulated over runs of equal src (rows are sorted by src)
-      float* srow = stage + r * STAGE_LD;
+      // stage the fp32 messages; each warp then walks its own 32 rows with row-wide accesses
+      float* stage = reinterpret_cast<float*>(pbuf);
 #pragma unroll
-      for (int q = 0; q < 32; ++q)
-        *reinterpret_cast<float2*>(srow + 2 * q) =
-            make_float2(v[2 * q] + bias.b[3][2 * q], v[2 * q + 1] + bias.b[3][2 * q + 1]);
-      __syncwarp();   // rows of a warp are staged and consumed by the same warp
-      const int64_t g0 = row0 + warp * 32;
-      int my_s = -1, my_d = -1;
-      if (g0 + lane < n_rows) {
-        my_s = a.src[g0 + lane];
-        my_d = a.dst[g0 + lane];
-      }
-      int cur_s = -1;
-      float2 acc = make_float2(0.f, 0.f);
-      for (int rr = 0; rr < 32; ++rr) {
-        const int s = __shfl_sync(0xffffffffu, my_s, rr);
-        const int d = __shfl_sync(0xffffffffu, my_d, rr);
-        if (s < 0) break;
-        const float2 m = *reinterpret_cast<const float2*>(stage + (warp * 32 + rr) * STAGE_LD + 2 * lane);
-        ptx::red_add_v2(a.xV + static_cast<int64_t>(d) * D + 2 * lane, m.x, m.y);
-        if (s != cur_s) {
-          if (cur_s >= 0) ptx::red_add_v2(a.xV + static_cast<int64_t>(cur_s) * D + 2 * lane, acc.x, acc.y);
-          cur_s = s;
-          acc = m;
-        } else {
-          acc.x += m.x;
-          acc.y += m.y;
-        }
-      }
-      if (cur_s >= 0) ptx::red_add_v2(a.xV + static_cast<int64_t>(cur_s) * D + 2 * lane, acc.x, acc.y);
+      for (int q = 0; q < 16; ++q)
+        *reinterpret_cast<float4*>(pbuf + stage_off(r, q)) =
+            make_float4(v[4 * q] + bias.b[3][4 * q], v[4 * q + 1] + bias.b[3][4 * q + 1],
+                        v[4 * q + 2] + bias.b[3][4 * q + 2], v[4 * q + 3] + bias.b[3][4 * q + 3]);
       __syncwarp();
+      const int64_t g0 = row0 + q4 * 32;
+      if (ROLE == 0) {
+        for (int rr = 0; rr < 32; ++rr) {
+          if (g0 + rr >= n_rows) break;
+          const int row = q4 * 32 + rr;
+          const float2 m = *reinterpret_cast<const float2*>(pbuf + stage_off(row, lane >> 1) + (lane & 1) * 8);
+          *reinterpret_cast<float2*>(a.mV + (g0 + rr) * D + 2 * lane) = m;
+        }
+      } else {
+        // dst side: one vector reduction per row; src side accumulated over runs of equal src
+        // (rows of a complete graph are sorted by src, instance_loader.py:60)
+        int my_s = -1, my_d = -1;
+        if (g0 + lane < n_rows) {
+          my_s = a.src[g0 + lane];
+          my_d = a.dst[g0 + lane];
+        }
+        int cur_s = -1;
+        float2 acc = make_float2(0.f, 0.f);
+        for (int rr = 0; rr < 32; ++rr) {
+          const int s = __shfl_sync(0xffffffffu, my_s, rr);
+          const int d = __shfl_sync(0xffffffffu, my_d, rr);
+          if (s < 0) break;
+          const int row = q4 * 32 + rr;
+          const float2 m = *reinterpret_cast<const float2*>(pbuf + stage_off(row, lane >> 1) + (lane & 1) * 8);
+          ptx::red_add_v2(a.xV + static_cast<int64_t>(d) * D + 2 * lane, m.x, m.y);
+          if (s != cur_s) {
+            if (cur_s >= 0) ptx::red_add_v2(a.xV + static_cast<int64_t>(cur_s) * D + 2 * lane, acc.x, acc.y);
+            cur_s = s;
+            acc = m;
+          } else {
+            acc.x += m.x;
+            acc.y += m.y;
+          }
+        }
+        if (cur_s >= 0) ptx::red_add_v2(a.xV + static_cast<int64_t>(cur_s) * D + 2 * lane, acc.x, acc.y);
+      }
+      (void)stage;
+      // the pong buffer is rewritten (in the operand layout) by this warpgroup's next tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+    }
+  }
+}
+
+template <int HP>
+__device__ __forceinline__ void k2_mma(const uint8_t* wimg, uint8_t* wsm, uint8_t* in_bufs, uint8_t* pbufs,
+                                       uint64_t* bar_w, uint64_t* in_full, uint64_t* in_free, uint64_t* acc_full,
+                                       uint64_t* act_ready, uint32_t tmem, int ntiles, int n_layers) {
+  using L = K2Smem<HP>;
+  constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 64);
+  ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+  for (int off = 0; off < L::W_BYTES; off += 16384) ptx::bulk_g2s(wsm + off, wimg + off, 16384, bar_w);
+  ptx::mbar_wait(bar_w, 0);
+  const int npairs = (ntiles + 1) >> 1;
+  for (int pi = 0; pi < npairs; ++pi) {
+    for (int l = 0; l < n_layers; ++l) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = 2 * pi + e;
+        if (n >= ntiles) continue;
+        const int slot = n % L::NIN;
+        const uint32_t step = static_cast<uint32_t>(pi * n_layers + l);
+        if (l == 0) ptx::mbar_wait(&in_full[slot], (n / L::NIN) & 1);
+        if (step > 0) ptx::mbar_wait(&act_ready[e], (step - 1) & 1);
+        ptx::tcgen05_fence_after();
+        const uint8_t* abuf = (l & 1) ? (pbufs + e * L::P_BYTES) : (in_bufs + slot * L::IN_BYTES);
+        uint32_t accumulate = 0;
+        constexpr int NCOMB = (HP == 2) ? 3 : 1;
+        const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
+#pragma unroll
+        for (int cb = 0; cb < NCOMB; ++cb) {
+          const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
+          const uint32_t abase = ptx::smem_u32(abuf + pa * PLANE_BYTES);
+          const uint32_t bbase = ptx::smem_u32(wsm + (l * HP + pb) * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ptx::umma_bf16_ss(tmem + e * 64, ptx::umma_desc_k_nosw(abase + k * 4096, 2048, 128),
+                              ptx::umma_desc_k_nosw(bbase + k * 2048, 1024, 128), IDESC, accumulate);
+            accumulate = 1;
+          }
+        }
+        ptx::umma_commit(&acc_full[e]);
+        if (l == 2) ptx::umma_commit(&in_free[slot]);   // last layer that reads the input slot
+      }
+    }
+  }
+}
+
+template <int HP>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
+  using L = K2Smem<HP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* wsm = smem;
+  uint8_t* in_bufs = smem + L::IN_OFF;
+  uint8_t* pbufs = smem + L::P_OFF;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* in_full = bar_w + 1;
+  uint64_t* in_free = in_full + L::NIN;
+  uint64_t* acc_full = in_free + L::NIN;
+  uint64_t* act_ready = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
+  int t0, t1;
+  if (is_v) tile_range(blockIdx.x - a.e_ctas, gridDim.x - a.e_ctas, a.tilesV, t0, t1);
+  else tile_range(blockIdx.x, a.e_ctas, a.tilesE, t0, t1);
+  const uint8_t* state = is_v ? a.stateV : a.stateE;
+  const int ntiles = t1 - t0;
+
+  if (tid == 0) {
+    ptx::mbar_init(bar_w, 1);
+    for (int s = 0; s < L::NIN; ++s) {
+      ptx::mbar_init(&in_full[s], 1);
+      ptx::mbar_init(&in_free[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&act_ready[s], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(tmem_slot, 128);
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    uint8_t* pbuf = pbufs + (warp >> 2) * L::P_BYTES;
+    if (a.vote_mode) k2_chain<HP, 2>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane);
+    else if (is_v) k2_chain<HP, 0>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane);
+    else k2_chain<HP, 1>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane);
+  } else if (warp == 8) {
+    if (lane == 0 && ntiles > 0)
+      k2_mma<HP>(is_v ? a.wV : a.wE, wsm, in_bufs, pbufs, bar_w, in_full, in_free, acc_full, act_ready, tmem, ntiles,
+                 a.vote_mode ? 3 : 4);
+  } else if (warp == 9) {
+    if (lane == 0) {
+      for (int n = 0; n < ntiles; ++n) {
+        const int slot = n % L::NIN, use = n / L::NIN;
+        if (use >= 1) ptx::mbar_wait(&in_free[slot], (use - 1) & 1);
+        ptx::mbar_arrive_expect_tx(&in_full[slot], L::IN_BYTES);
+        ptx::bulk_g2s(in_bufs + slot * L::IN_BYTES, state + static_cast<int64_t>(t0 + n) * tile_bytes(HP), L::IN_BYTES,
+                      &in_full[slot]);
+      }
     }
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 64);
+  if (warp == 8) ptx::tmem_dealloc(tmem, 128);
 }
 
 // ====================================================================================
@@ -515,13 +677,13 @@ __global__ void __launch_bounds__(256) tc_pack_state_kernel(const float* __restr
     if (row < n_rows) hv = *reinterpret_cast<const float2*>(h + row * D + col);
     uint32_t hi, lo;
     ptx::split_bf16x2(hv.x, hv.y, hi, lo);
-    *reinterpret_cast<uint32_t*>(tile + img16_off(r, col)) = hi;
-    if (HP == 2) *reinterpret_cast<uint32_t*>(tile + IMG16_BYTES + img16_off(r, col)) = lo;
+    *reinterpret_cast<uint32_t*>(tile + plane_off(r, col)) = hi;
+    if (HP == 2) *reinterpret_cast<uint32_t*>(tile + PLANE_BYTES + plane_off(r, col)) = lo;
   }
   if (c) {
     float2 cv = make_float2(0.f, 0.f);
     if (row < n_rows) cv = *reinterpret_cast<const float2*>(c + row * D + col);
-    *reinterpret_cast<float2*>(tile + HP * IMG16_BYTES + img32_off(r, col)) = cv;
+    *reinterpret_cast<float2*>(tile + HP * PLANE_BYTES + ct_off(r, col)) = cv;
   }
 }
 
@@ -530,9 +692,9 @@ template <int HP>
 __global__ void __launch_bounds__(256) tc_zero_c_kernel(int64_t n_rows_pad, uint8_t* __restrict__ state) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index
   if (i >= n_rows_pad * 16) return;
-  const int64_t row = i >> 4;
-  uint8_t* tile = state + (row / TILE_ROWS) * tile_bytes(HP) + HP * IMG16_BYTES;
-  reinterpret_cast<float4*>(tile)[(row % TILE_ROWS) * 16 + (i & 15)] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t tile = i / (TILE_ROWS * 16);
+  reinterpret_cast<float4*>(state + tile * tile_bytes(HP) + HP * PLANE_BYTES)[i % (TILE_ROWS * 16)] =
+      make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 template <int HP>
@@ -545,17 +707,17 @@ __global__ void __launch_bounds__(256) tc_unpack_state_kernel(const uint8_t* __r
   const uint8_t* tile = state + (row / TILE_ROWS) * tile_bytes(HP);
   const int r = static_cast<int>(row % TILE_ROWS);
   if (h) {
-    const uint32_t hi = *reinterpret_cast<const uint32_t*>(tile + img16_off(r, col));
+    const uint32_t hi = *reinterpret_cast<const uint32_t*>(tile + plane_off(r, col));
     float x0 = __uint_as_float(hi << 16), x1 = __uint_as_float(hi & 0xFFFF0000u);
     if (HP == 2) {
-      const uint32_t lo = *reinterpret_cast<const uint32_t*>(tile + IMG16_BYTES + img16_off(r, col));
+      const uint32_t lo = *reinterpret_cast<const uint32_t*>(tile + PLANE_BYTES + plane_off(r, col));
       x0 += __uint_as_float(lo << 16);
       x1 += __uint_as_float(lo & 0xFFFF0000u);
     }
     *reinterpret_cast<float2*>(h + row * D + col) = make_float2(x0, x1);
   }
   if (c) *reinterpret_cast<float2*>(c + row * D + col) =
-      *reinterpret_cast<const float2*>(tile + HP * IMG16_BYTES + img32_off(r, col));
+      *reinterpret_cast<const float2*>(tile + HP * PLANE_BYTES + ct_off(r, col));
 }
 
 }  // namespace tspgnn

@@ -102,6 +102,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Same descriptor for the un-swizzled ("interleaved") K-major canonical layout, in 16-byte
+// units ((8,n),2):((1,SBO),LBO): a core matrix is 8 rows x 16 B stored contiguously (128 B),
+// 8-row groups are SBO bytes apart and the two 16-byte K chunks of one MMA are LBO bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_k_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address      [0,14)
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;          // LBO                [16,30)
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;          // SBO                [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version [46,48)
+  return d;                                                  // layout type 0 = SWIZZLE_NONE
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16 with bf16 A/B, fp32 D,
 // both operands K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
@@ -187,6 +199,45 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// three 16-column loads in flight, one wait (the i / j / f gate chunks of a row)
+__device__ __forceinline__ void tmem_ld16x3(uint32_t a0, uint32_t a1, uint32_t a2, float (&v0)[16], float (&v1)[16],
+                                            float (&v2)[16]) {
+  uint32_t r[48];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%48];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%49];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47}, [%50];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+      : "r"(a0), "r"(a1), "r"(a2)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v0[i] = __uint_as_float(r[i]);
+    v1[i] = __uint_as_float(r[16 + i]);
+    v2[i] = __uint_as_float(r[32 + i]);
+  }
+}
+
+// ------------------------------- register re-allocation ------------------------------
+// executed by every warp of a warpgroup (4 consecutive warps, first one a multiple of 4)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ------------------------------- misc ----------------------------------------------

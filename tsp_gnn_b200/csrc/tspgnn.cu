@@ -100,14 +100,15 @@ float bf16_to_f(uint16_t h) {
 }
 
 // B-operand image of W[k0:k0+64, n0:n0+nrows] (tf kernel layout [in,out], leading dim ldw):
-// image row n holds the 64 k-values of output feature n (K-major), 128-B swizzled rows.
+// output feature n, k-value k at wimg_off(n, k, nrows) -- the un-swizzled K-major layout the
+// kernels describe with LBO = nrows*16, SBO = 128.
 void make_b_image(const float* W, int ldw, int k0, int n0, int nrows, int plane, uint8_t* img) {
   for (int n = 0; n < nrows; ++n)
     for (int k = 0; k < 64; ++k) {
       const float w = W[static_cast<int64_t>(k0 + k) * ldw + n0 + n];
       const uint16_t hi = bf16_rn(w);
       const uint16_t val = plane == 0 ? hi : bf16_rn(w - bf16_to_f(hi));
-      memcpy(img + img16_off(n, k), &val, 2);
+      memcpy(img + wimg_off(n, k, nrows), &val, 2);
     }
 }
 
@@ -455,7 +456,7 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote) {
   a.vote_mode = vote ? 1 : 0;
   int grid;
   role_split(h, a.tilesE, a.tilesV, grid, a.e_ctas);
-  tc_mlp_kernel<HP><<<grid, 128, K2Smem<HP>::DYN_BYTES, s>>>(a);
+  tc_mlp_kernel<HP><<<grid, TC_THREADS, K2Smem<HP>::DYN_BYTES, s>>>(a);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -477,7 +478,7 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s) {
   a.tilesV = h->tilesV;
   int grid;
   role_split(h, a.tilesE, a.tilesV, grid, a.e_ctas);
-  tc_lnlstm_kernel<HP><<<grid, 128, K1Smem<HP>::DYN_BYTES, s>>>(a);
+  tc_lnlstm_kernel<HP><<<grid, TC_THREADS, K1Smem<HP>::DYN_BYTES, s>>>(a);
   LAUNCH_CHECK(h);
   return 0;
 }
