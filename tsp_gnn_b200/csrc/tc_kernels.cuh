@@ -255,6 +255,30 @@ __device__ __forceinline__ void k1_mma(const uint8_t* wimg, uint8_t* wsm, uint8_
 }
 
 // ---- epilogue: thread r owns row r (TMEM lane r) of the tiles of its warpgroup -----------
+// Loops are kept rolled on purpose: the epilogue is the instruction-heavy part of the step and a
+// fully unrolled version (60 KB of SASS per role) was instruction-fetch bound.  The FMA-pipe math
+// uses packed fp32x2 instructions (FFMA2 / FADD2 / FMUL2).
+
+// two-pass mean / inverse standard deviation of 64 TMEM columns of this thread's row
+// (nn.moments semantics); returns rstd and nmr = -mean * rstd so that LN(v) = fma(v, rstd, nmr)
+__device__ __forceinline__ void row_stats64(uint32_t taddr, float& rstd, float& nmr) {
+  float v[64];
+  ptx::tmem_ld64(taddr, v);
+  float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s2 = __fadd2_rn(s2, make_float2(v[2 * j], v[2 * j + 1]));
+  const float m = (s2.x + s2.y) * (1.0f / 64);
+  const float2 nm2 = make_float2(-m, -m);
+  float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float2 t = __fadd2_rn(make_float2(v[2 * j], v[2 * j + 1]), nm2);
+    q2 = __ffma2_rn(t, t, q2);
+  }
+  rstd = rsqrtf((q2.x + q2.y) * (1.0f / 64) + LN_EPS);
+  nmr = -m * rstd;
+}
+
 template <int HP, int CELL>
 __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
                                             uint64_t* acc_empty, int warp, int lane) {
@@ -267,94 +291,92 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
     uint8_t* gtile = state + static_cast<int64_t>(t0 + n) * tile_bytes(HP);
     float4* cg = reinterpret_cast<float4*>(gtile + HP * PLANE_BYTES) + r;   // chunk q at cg[q * 128]
     uint4* hg = reinterpret_cast<uint4*>(gtile) + r;                        // plane p, chunk ch at hg[p*1024 + ch*128]
-    // old cell state: issued before the accumulator is ready so the latency hides behind the MMA
-    float cn[64];
+    // first 16 columns of the old cell state: issued before the accumulator is ready
+    float4 cur[4];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const float4 t = cg[q * 128];
-      cn[4 * q] = t.x; cn[4 * q + 1] = t.y; cn[4 * q + 2] = t.z; cn[4 * q + 3] = t.w;
-    }
+    for (int q = 0; q < 4; ++q) cur[q] = cg[q * 128];
     ptx::mbar_wait(&acc_full[e], use & 1);
     ptx::tcgen05_fence_after();
 
-    float mu[4], rs[4];
-#pragma unroll
+    // ---- LayerNorm statistics of the four gates ------------------------------------------
+    float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f, mu0 = 0.f, mu1 = 0.f, mu2 = 0.f, mu3 = 0.f;
+#pragma unroll 1
     for (int g = 0; g < 4; ++g) {
-      float v[64];
-      ptx::tmem_ld64(t_acc + g * 64, v);
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) s += v[j];
-      const float m = s * (1.0f / 64);
-      float q = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float t = v[j] - m;
-        q = fmaf(t, t, q);
-      }
-      const float rstd = rsqrtf(q * (1.0f / 64) + LN_EPS);
-      rs[g] = rstd;
-      mu[g] = -m * rstd;          // (v - m) * rstd = fma(v, rstd, -m * rstd)
+      float rstd, nmr;
+      row_stats64(t_acc + g * 64, rstd, nmr);
+      if (g == 0) { rs0 = rstd; mu0 = nmr; }
+      else if (g == 1) { rs1 = rstd; mu1 = nmr; }
+      else if (g == 2) { rs2 = rstd; mu2 = nmr; }
+      else { rs3 = rstd; mu3 = nmr; }
     }
-#pragma unroll
+    // ---- new cell state before its LayerNorm; parked in the (consumed) i-gate columns -------
+#pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
-      float vi[16], vj[16], vf[16];
+      float4 nxt[4];
+      const int cn_ = (cc < 3) ? cc + 1 : cc;            // prefetch the next 16 columns of c
+#pragma unroll
+      for (int q = 0; q < 4; ++q) nxt[q] = cg[(cn_ * 4 + q) * 128];
+      float vi[16], vj[16], vf[16], cnew[16];
       ptx::tmem_ld16x3(t_acc + 0 * 64 + cc * 16, t_acc + 1 * 64 + cc * 16, t_acc + 2 * 64 + cc * 16, vi, vj, vf);
+      const float2* gi = reinterpret_cast<const float2*>(ln.gamma[0] + cc * 16);
+      const float2* bi = reinterpret_cast<const float2*>(ln.beta[0] + cc * 16);
+      const float2* gj = reinterpret_cast<const float2*>(ln.gamma[1] + cc * 16);
+      const float2* bj = reinterpret_cast<const float2*>(ln.beta[1] + cc * 16);
+      const float2* gf = reinterpret_cast<const float2*>(ln.gamma[2] + cc * 16);
+      const float2* bf = reinterpret_cast<const float2*>(ln.beta[2] + cc * 16);
 #pragma unroll
-      for (int el = 0; el < 16; ++el) {
-        const int j = cc * 16 + el;
-        const float in = fmaf(fmaf(vi[el], rs[0], mu[0]), ln.gamma[0][j], ln.beta[0][j]);
-        const float jn = fmaf(fmaf(vj[el], rs[1], mu[1]), ln.gamma[1][j], ln.beta[1][j]);
-        const float fn = fmaf(fmaf(vf[el], rs[2], mu[2]), ln.gamma[2][j], ln.beta[2][j]) + FORGET_BIAS;
-        cn[j] = fmaf(cn[j], fast_sigmoid(fn), fast_sigmoid(in) * fmaxf(jn, 0.f));
+      for (int p = 0; p < 8; ++p) {
+        const float2 in = __ffma2_rn(__ffma2_rn(make_float2(vi[2 * p], vi[2 * p + 1]), make_float2(rs0, rs0),
+                                                make_float2(mu0, mu0)), gi[p], bi[p]);
+        const float2 jn = __ffma2_rn(__ffma2_rn(make_float2(vj[2 * p], vj[2 * p + 1]), make_float2(rs1, rs1),
+                                                make_float2(mu1, mu1)), gj[p], bj[p]);
+        const float2 fn = __fadd2_rn(__ffma2_rn(__ffma2_rn(make_float2(vf[2 * p], vf[2 * p + 1]), make_float2(rs2, rs2),
+                                                           make_float2(mu2, mu2)), gf[p], bf[p]),
+                                     make_float2(FORGET_BIAS, FORGET_BIAS));
+        const float4 c4 = cur[p >> 1];
+        const float2 cold = (p & 1) ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
+        const float2 cn2 = __ffma2_rn(cold, ptx::sigmoid2(fn), __fmul2_rn(ptx::sigmoid2(in), ptx::relu2(jn)));
+        cnew[2 * p] = cn2.x;
+        cnew[2 * p + 1] = cn2.y;
       }
+      ptx::tmem_st16(t_acc + cc * 16, cnew);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
     }
-    float cm, crs;
-    {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) s += cn[j];
-      const float m = s * (1.0f / 64);
-      float q = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float t = cn[j] - m;
-        q = fmaf(t, t, q);
-      }
-      crs = rsqrtf(q * (1.0f / 64) + LN_EPS);
-      cm = -m * crs;
-    }
-#pragma unroll
+    float crs, cm;
+    row_stats64(t_acc, crs, cm);
+    // ---- LayerNorm of the cell state, output gate, new h; straight to global memory -------------
+#pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
-      float vo[16], hn[16];
-      ptx::tmem_ld16(t_acc + 3 * 64 + cc * 16, vo);
+      float vo[16], cs[16];
+      ptx::tmem_ld16x2(t_acc + 3 * 64 + cc * 16, t_acc + cc * 16, vo, cs);
       if (cc == 3) {     // last TMEM read of this tile: hand the accumulator back to the MMA warp
         ptx::tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[e]);
       }
+      const float2* go = reinterpret_cast<const float2*>(ln.gamma[3] + cc * 16);
+      const float2* bo = reinterpret_cast<const float2*>(ln.beta[3] + cc * 16);
+      const float2* gs = reinterpret_cast<const float2*>(ln.gamma[4] + cc * 16);
+      const float2* bs = reinterpret_cast<const float2*>(ln.beta[4] + cc * 16);
+      float2 c2[8];
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int el = 0; el < 16; ++el) {
-        const int j = cc * 16 + el;
-        const float on = fmaf(fmaf(vo[el], rs[3], mu[3]), ln.gamma[3][j], ln.beta[3][j]);
-        const float c2 = fmaf(fmaf(cn[j], crs, cm), ln.gamma[4][j], ln.beta[4][j]);
-        cn[j] = c2;
-        hn[el] = fmaxf(c2, 0.f) * fast_sigmoid(on);
+      for (int p = 0; p < 8; ++p) {
+        const float2 on = __ffma2_rn(__ffma2_rn(make_float2(vo[2 * p], vo[2 * p + 1]), make_float2(rs3, rs3),
+                                                make_float2(mu3, mu3)), go[p], bo[p]);
+        c2[p] = __ffma2_rn(__ffma2_rn(make_float2(cs[2 * p], cs[2 * p + 1]), make_float2(crs, crs),
+                                      make_float2(cm, cm)), gs[p], bs[p]);
+        const float2 hn = __fmul2_rn(ptx::relu2(c2[p]), ptx::sigmoid2(on));
+        ptx::split_bf16x2_p(hn, hi[p], lo[p]);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int j = cc * 16 + q * 4;
-        cg[(cc * 4 + q) * 128] = make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]);
-      }
+      for (int q = 0; q < 4; ++q)
+        cg[(cc * 4 + q) * 128] = make_float4(c2[2 * q].x, c2[2 * q].y, c2[2 * q + 1].x, c2[2 * q + 1].y);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {   // two 16-B chunks of 8 bf16
-        float x[8];
-#pragma unroll
-        for (int p = 0; p < 8; ++p) x[p] = hn[q * 8 + p];
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        hg[(cc * 2 + q) * 128] = hi;
-        if (HP == 2) hg[1024 + (cc * 2 + q) * 128] = lo;
+        hg[(cc * 2 + q) * 128] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        if (HP == 2) hg[1024 + (cc * 2 + q) * 128] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
       }
     }
   }
@@ -458,7 +480,7 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
     const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
     uint8_t* ibuf = in_bufs + (n % L::NIN) * L::IN_BYTES;
     float v[64];
-#pragma unroll
+#pragma unroll 1
     for (int l = 0; l < NL; ++l, ++step) {
       ptx::mbar_wait(&acc_full[e], step & 1);
       ptx::tcgen05_fence_after();
@@ -467,21 +489,22 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
       const bool feeds_mma = l < NL - 1;
       if (hidden) {
         uint8_t* nxt = (l & 1) ? ibuf : pbuf;     // layer l reads (l even ? in : pong), writes the other
+        const float2* b2 = reinterpret_cast<const float2*>(bias.b[l]);
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-          float x[8];
+          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const int j = ch * 8 + p;
-            x[p] = fmaxf(v[j] + bias.b[l][j], 0.f);
-            v[j] = x[p];
+          for (int p = 0; p < 4; ++p) {
+            const int j = ch * 8 + 2 * p;
+            const float2 x = ptx::relu2(__fadd2_rn(make_float2(v[j], v[j + 1]), b2[ch * 4 + p]));
+            v[j] = x.x;
+            v[j + 1] = x.y;
+            ptx::split_bf16x2_p(x, hi[p], lo[p]);
           }
           if (feeds_mma) {
-            uint4 hi, lo;
-            split8(x, hi, lo);
             const uint32_t off = ch * 2048 + r * 16;
-            *reinterpret_cast<uint4*>(nxt + off) = hi;
-            if (HP == 2) *reinterpret_cast<uint4*>(nxt + PLANE_BYTES + off) = lo;
+            *reinterpret_cast<uint4*>(nxt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (HP == 2) *reinterpret_cast<uint4*>(nxt + PLANE_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
         if (feeds_mma) ptx::fence_proxy_async_smem();

@@ -229,6 +229,41 @@ __device__ __forceinline__ void tmem_ld16x3(uint32_t a0, uint32_t a1, uint32_t a
   }
 }
 
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t a0, uint32_t a1, float (&v0)[16], float (&v1)[16]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(a0), "r"(a1)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v0[i] = __uint_as_float(r[i]);
+    v1[i] = __uint_as_float(r[16 + i]);
+  }
+}
+
+// registers -> 16 TMEM columns of this thread's lane (32x32b), completed before returning
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n\t"
+      "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+
 // ------------------------------- register re-allocation ------------------------------
 // executed by every warp of a warpgroup (4 consecutive warps, first one a multiple of 4)
 template <int N>
@@ -253,6 +288,33 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   float ah = __uint_as_float(hi << 16);
   float bh = __uint_as_float(hi & 0xFFFF0000u);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
+
+// ------------------------------- fast math -------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// logistic function of two values: 1 / (1 + 2^(-x log2 e)); packed fp32x2 for the FMA-pipe part
+__device__ __forceinline__ float2 sigmoid2(float2 x) {
+  const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
+  return make_float2(rcp_approx(e.x), rcp_approx(e.y));
+}
+__device__ __forceinline__ float2 relu2(float2 x) { return make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)); }
+
+// fp32 pair -> bf16x2 hi and bf16x2 lo = rn(x - hi) (packed subtract)
+__device__ __forceinline__ void split_bf16x2_p(float2 x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x.y), "f"(x.x));
+  const float2 h = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+  const float2 d = __ffma2_rn(h, make_float2(-1.0f, -1.0f), x);   // x - hi, exact
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
 }
 
 }  // namespace ptx
