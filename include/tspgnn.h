@@ -105,6 +105,10 @@ int64_t tspgnn_launch_count(tspgnn_handle h);
  * (K2).  Tensor-core modes only.  The recurrent state keeps evolving while this runs. */
 int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* mean_ms, void* stream);
 
+/* Development aid: one launch of K1 (which = 0) or K2 (which = 1) with a clock64() trace of the
+ * warp roles, copied to out_host[cta][role][tile][event] (148*4*64*8 int64). */
+int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_host, int64_t n_int64, void* stream);
+
 /* Host helper: dense EV (row-major [rows, cols], float64 or float32 by elem_size 8/4) ->
  * edge_src/edge_dst (instance_loader.py:63-66 layout).  Returns TSPGNN_E_INVALID if a row
  * does not have exactly two non-zeros. */

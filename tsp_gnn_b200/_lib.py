@@ -43,6 +43,8 @@ SIGNATURES = [
     ("tspgnn_launch_count", ctypes.c_int64, [ctypes.c_void_p]),
     ("tspgnn_time_kernel", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
+    ("tspgnn_debug_timeline", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                             ctypes.c_void_p]),
     ("tspgnn_dense_ev_to_coo", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                               ctypes.c_void_p, ctypes.c_void_p]),
 ]

@@ -65,6 +65,7 @@ struct K1Args {
   const int32_t* dst;
   int64_t nE, nV;
   int tilesE, tilesV, e_ctas;
+  long long* timeline;   // optional clock64() trace (tools/timeline.py), nullptr in production
 };
 
 struct K2Args {
@@ -80,7 +81,15 @@ struct K2Args {
   int64_t nE, nV;
   int tilesE, tilesV, e_ctas;
   int vote_mode;
+  long long* timeline;
 };
+
+// timeline slot: [cta][role 0..3][local tile 0..63][event 0..7]
+constexpr int TL_ROLES = 4, TL_TILES = 64, TL_EVENTS = 8;
+__device__ __forceinline__ void tl_mark(long long* tl, int role, int tile, int ev) {
+  if (tl != nullptr && tile < TL_TILES)
+    tl[((static_cast<int64_t>(blockIdx.x) * TL_ROLES + role) * TL_TILES + tile) * TL_EVENTS + ev] = clock64();
+}
 
 // contiguous, balanced range of tiles for CTA `i` of `n`
 __device__ __forceinline__ void tile_range(int i, int n, int tiles, int& t0, int& t1) {
@@ -107,9 +116,11 @@ struct K1Smem {
   static constexpr int RING_OFF = W_BYTES;
   static constexpr int BAR_OFF = RING_OFF + NSLOT * SLOT_BYTES;
   static constexpr int NBAR = 1 + 2 * NSLOT + 4;
-  static constexpr int TOTAL = BAR_OFF + 8 * NBAR + 16;
+  static constexpr int LN_OFF = (BAR_OFF + 8 * NBAR + 16 + 15) & ~15;   // gamma[5][64], beta[5][64] of this CTA's cell
+  static constexpr int TOTAL = LN_OFF + 2 * 5 * D * 4;
   static constexpr int DYN_BYTES = TOTAL + 128;            // slack for 128-B alignment
 };
+static_assert(K1Smem<2>::DYN_BYTES <= 232448, "K1 shared memory budget (227 KB)");
 
 // ---- producer: build the x operand of one tile in shared memory ------------------------
 // E rows: x = mV[src] + mV[dst] (= EV . msg, model.py:85-91); V rows: x = xV (then cleared).
@@ -119,6 +130,7 @@ template <int HP, bool IS_V>
 __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64_t row0, const float* __restrict__ mV,
                                           float* __restrict__ xV, const int (&si)[6], const int (&di)[6]) {
   const int r8 = lane & 7, cq = lane >> 3;
+  const uint32_t slot_s = ptx::smem_u32(slot);
 #pragma unroll
   for (int gi = 0; gi < 6; ++gi) {
     const int g = gw + NUM_GATHER_WARPS * gi;
@@ -144,9 +156,9 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
         }
         uint4 hi, lo;
         split8(x, hi, lo);
-        const uint32_t off = chunk * 2048 + row * 16;
-        *reinterpret_cast<uint4*>(slot + off) = hi;
-        if (HP == 2) *reinterpret_cast<uint4*>(slot + PLANE_BYTES + off) = lo;
+        const uint32_t off = slot_s + chunk * 2048 + row * 16;
+        ptx::sts128(off, hi);
+        if (HP == 2) ptx::sts128(off + PLANE_BYTES, lo);
       }
     }
   }
@@ -156,6 +168,7 @@ template <int HP, bool IS_V>
 __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uint8_t* ring, uint64_t* full,
                                             uint64_t* empty, int t0, int ntiles, int gw, int lane) {
   using L = K1Smem<HP>;
+  long long* tl = (gw == 0 && lane == 0) ? a.timeline : nullptr;
   const int r8 = lane & 7;
   int si[6], di[6];
 #pragma unroll
@@ -182,12 +195,15 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
 #pragma unroll
       for (int gi = 0; gi < 6; ++gi) sn[gi] = dn[gi] = 0;
       if (n + 1 < ntiles) load_idx(tile + 1, sn, dn);     // next tile's column indices, a tile ahead
+      tl_mark(tl, 3, n, 0);
       if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
+      tl_mark(tl, 3, n, 1);
       k1_fill_x<HP, IS_V>(ring + slot * L::SLOT_BYTES, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, a.mV, a.xV,
                           si, di);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full[slot]);
+      tl_mark(tl, 3, n, 2);
 #pragma unroll
       for (int gi = 0; gi < 6; ++gi) {
         si[gi] = sn[gi];
@@ -198,6 +214,7 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
     {
       const int seq = 2 * n + 1, slot = seq % L::NSLOT, use = seq / L::NSLOT;
       if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
+      tl_mark(tl, 3, n, 3);
       if (lane == 0) {
         if (gw == 0) {
           ptx::mbar_arrive_expect_tx(&full[slot], L::SLOT_BYTES);
@@ -213,44 +230,57 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
 }
 
 // ---- MMA issuer: z[128 x 256] = [x,h] . K, accumulators alternate between two TMEM halves ----
+// Executed by the whole warp (converged); one elected lane issues the tcgen05 instructions.
 template <int HP>
 __device__ __forceinline__ void k1_mma(const uint8_t* wimg, uint8_t* wsm, uint8_t* ring, uint64_t* bar_w,
                                        uint64_t* full, uint64_t* empty, uint64_t* acc_full, uint64_t* acc_empty,
-                                       uint32_t tmem, int ntiles) {
+                                       uint32_t tmem, int ntiles, long long* tl_) {
   using L = K1Smem<HP>;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 256);
-  ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-  for (int off = 0; off < L::W_BYTES; off += 32768) ptx::bulk_g2s(wsm + off, wimg + off, 32768, bar_w);
+  const bool leader = ptx::elect_one();
+  long long* tl = leader ? tl_ : nullptr;
+  if (leader) {
+    ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+    for (int off = 0; off < L::W_BYTES; off += 32768) ptx::bulk_g2s(wsm + off, wimg + off, 32768, bar_w);
+  }
+  __syncwarp();
   ptx::mbar_wait(bar_w, 0);
+  // descriptors of the first k-step of (ring slot 0, plane 0) and of (weight plane 0, k-block 0);
+  // everything else is an offset in 16-byte units added to the low word
+  const uint64_t adesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(ring), 2048, 128);
+  const uint64_t bdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(wsm), 4096, 128);
   for (int n = 0; n < ntiles; ++n) {
     const int acc = n & 1, k_use = n >> 1;
+    tl_mark(tl, 2, n, 0);
     if (k_use >= 1) ptx::mbar_wait(&acc_empty[acc], (k_use - 1) & 1);
-    ptx::tcgen05_fence_after();
+    tl_mark(tl, 2, n, 1);
     const uint32_t d_tmem = tmem + acc * 256;
-    uint32_t accumulate = 0;
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb) {
       const int seq = 2 * n + kb, slot = seq % L::NSLOT, use = seq / L::NSLOT;
       ptx::mbar_wait(&full[slot], use & 1);
+      tl_mark(tl, 2, n, 2 + 2 * kb);
       ptx::tcgen05_fence_after();
-      // (A plane, B plane): small cross terms first, then hi*hi
-      constexpr int NCOMB = (HP == 2) ? 3 : 1;
-      const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
+      if (ptx::elect_one()) {
+        // (A plane, B plane): small cross terms first, then hi*hi
+        constexpr int NCOMB = (HP == 2) ? 3 : 1;
+        const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
+        const uint64_t aslot = adesc0 + static_cast<uint32_t>((slot * L::SLOT_BYTES) >> 4);
 #pragma unroll
-      for (int cb = 0; cb < NCOMB; ++cb) {
-        const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
-        const uint32_t abase = ptx::smem_u32(ring + slot * L::SLOT_BYTES + pa * PLANE_BYTES);
-        const uint32_t bbase = ptx::smem_u32(wsm + (pb * 2 + kb) * 32768);
+        for (int cb = 0; cb < NCOMB; ++cb) {
+          const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          ptx::umma_bf16_ss(d_tmem, ptx::umma_desc_k_nosw(abase + k * 4096, 2048, 128),
-                            ptx::umma_desc_k_nosw(bbase + k * 8192, 4096, 128), IDESC, accumulate);
-          accumulate = 1;
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ss(d_tmem, aslot + ((pa * PLANE_BYTES + k * 4096) >> 4),
+                              bdesc0 + (((pb * 2 + kb) * 32768 + k * 8192) >> 4), IDESC,
+                              (kb | cb | k) ? 1u : 0u);
         }
+        ptx::umma_commit(&empty[slot]);
+        if (kb == 1) ptx::umma_commit(&acc_full[acc]);
       }
-      ptx::umma_commit(&empty[slot]);
+      __syncwarp();
+      tl_mark(tl, 2, n, 3 + 2 * kb);
     }
-    ptx::umma_commit(&acc_full[acc]);
   }
 }
 
@@ -264,38 +294,59 @@ __device__ __forceinline__ void k1_mma(const uint8_t* wimg, uint8_t* wsm, uint8_
 __device__ __forceinline__ void row_stats64(uint32_t taddr, float& rstd, float& nmr) {
   float v[64];
   ptx::tmem_ld64(taddr, v);
-  float2 s2 = make_float2(0.f, 0.f);
+  float2 s2[4];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) s2 = __fadd2_rn(s2, make_float2(v[2 * j], v[2 * j + 1]));
-  const float m = (s2.x + s2.y) * (1.0f / 64);
+  for (int k = 0; k < 4; ++k) s2[k] = make_float2(v[2 * k], v[2 * k + 1]);
+#pragma unroll
+  for (int j = 4; j < 32; ++j) s2[j & 3] = __fadd2_rn(s2[j & 3], make_float2(v[2 * j], v[2 * j + 1]));
+  const float2 st = __fadd2_rn(__fadd2_rn(s2[0], s2[1]), __fadd2_rn(s2[2], s2[3]));
+  const float m = (st.x + st.y) * (1.0f / 64);
   const float2 nm2 = make_float2(-m, -m);
-  float2 q2 = make_float2(0.f, 0.f);
+  float2 q2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q2[k] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float2 t = __fadd2_rn(make_float2(v[2 * j], v[2 * j + 1]), nm2);
-    q2 = __ffma2_rn(t, t, q2);
+    q2[j & 3] = __ffma2_rn(t, t, q2[j & 3]);
   }
-  rstd = rsqrtf((q2.x + q2.y) * (1.0f / 64) + LN_EPS);
+  const float2 qt = __fadd2_rn(__fadd2_rn(q2[0], q2[1]), __fadd2_rn(q2[2], q2[3]));
+  rstd = rsqrtf((qt.x + qt.y) * (1.0f / 64) + LN_EPS);
   nmr = -m * rstd;
+}
+
+// 1 + 2^t for two values (t = -x log2 e, so this is 1 + exp(-x)); the exponent is clamped so that
+// a product of two results stays finite
+__device__ __forceinline__ float2 one_plus_ex2(float2 t) {
+  return __fadd2_rn(make_float2(ptx::ex2_approx(fminf(t.x, 60.f)), ptx::ex2_approx(fminf(t.y, 60.f))),
+                    make_float2(1.0f, 1.0f));
 }
 
 template <int HP, int CELL>
 __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
-                                            uint64_t* acc_empty, int warp, int lane) {
+                                            uint64_t* acc_empty, int warp, int lane, long long* tl_, uint32_t ln_s) {
+  // ln_s: shared-memory copy of this cell's LayerNorm parameters, gamma[g][j] at ln_s + (g*64+j)*4,
+  // beta at +1280.  (Run-time indexed constant-bank loads cost ~10 cycles each; a broadcast
+  // LDS.128 brings four values in ~2.)
   const int e = warp >> 2, q4 = warp & 3;
+  long long* tl = (q4 == 0 && lane == 0) ? tl_ : nullptr;
   const int r = q4 * 32 + lane;
   const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 256;
-  const CellLN& ln = c_ln[CELL];
   int use = 0;
   for (int n = e; n < ntiles; n += 2, ++use) {
     uint8_t* gtile = state + static_cast<int64_t>(t0 + n) * tile_bytes(HP);
     float4* cg = reinterpret_cast<float4*>(gtile + HP * PLANE_BYTES) + r;   // chunk q at cg[q * 128]
     uint4* hg = reinterpret_cast<uint4*>(gtile) + r;                        // plane p, chunk ch at hg[p*1024 + ch*128]
-    // first 16 columns of the old cell state: issued before the accumulator is ready
-    float4 cur[4];
+    // first 32 columns of the old cell state: issued before the accumulator is ready
+    float4 cur[4], nx1[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cur[q] = cg[q * 128];
+    for (int q = 0; q < 4; ++q) {
+      cur[q] = cg[q * 128];
+      nx1[q] = cg[(4 + q) * 128];
+    }
+    tl_mark(tl, e, n, 0);
     ptx::mbar_wait(&acc_full[e], use & 1);
+    tl_mark(tl, e, n, 1);
     ptx::tcgen05_fence_after();
 
     // ---- LayerNorm statistics of the four gates ------------------------------------------
@@ -309,42 +360,65 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
       else if (g == 2) { rs2 = rstd; mu2 = nmr; }
       else { rs3 = rstd; mu3 = nmr; }
     }
+    tl_mark(tl, e, n, 2);
     // ---- new cell state before its LayerNorm; parked in the (consumed) i-gate columns -------
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
-      float4 nxt[4];
-      const int cn_ = (cc < 3) ? cc + 1 : cc;            // prefetch the next 16 columns of c
+      float4 nx2[4];
+      const int cn_ = (cc < 2) ? cc + 2 : cc;            // prefetch the 16 columns of c needed two iterations ahead
 #pragma unroll
-      for (int q = 0; q < 4; ++q) nxt[q] = cg[(cn_ * 4 + q) * 128];
+      for (int q = 0; q < 4; ++q) nx2[q] = cg[(cn_ * 4 + q) * 128];
       float vi[16], vj[16], vf[16], cnew[16];
+      float4 gq[6];
       ptx::tmem_ld16x3(t_acc + 0 * 64 + cc * 16, t_acc + 1 * 64 + cc * 16, t_acc + 2 * 64 + cc * 16, vi, vj, vf);
-      const float2* gi = reinterpret_cast<const float2*>(ln.gamma[0] + cc * 16);
-      const float2* bi = reinterpret_cast<const float2*>(ln.beta[0] + cc * 16);
-      const float2* gj = reinterpret_cast<const float2*>(ln.gamma[1] + cc * 16);
-      const float2* bj = reinterpret_cast<const float2*>(ln.beta[1] + cc * 16);
-      const float2* gf = reinterpret_cast<const float2*>(ln.gamma[2] + cc * 16);
-      const float2* bf = reinterpret_cast<const float2*>(ln.beta[2] + cc * 16);
+      const uint32_t lcc = ln_s + cc * 64;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
+        float4 Gi, Bi, Gj, Bj, Gf, Bf;
+        if ((p & 1) == 0) {
+          Gi = ptx::lds128f(lcc + 0 * 256 + (p >> 1) * 16);
+          Bi = ptx::lds128f(lcc + 1280 + 0 * 256 + (p >> 1) * 16);
+          Gj = ptx::lds128f(lcc + 1 * 256 + (p >> 1) * 16);
+          Bj = ptx::lds128f(lcc + 1280 + 1 * 256 + (p >> 1) * 16);
+          Gf = ptx::lds128f(lcc + 2 * 256 + (p >> 1) * 16);
+          Bf = ptx::lds128f(lcc + 1280 + 2 * 256 + (p >> 1) * 16);
+          gq[0] = Gi; gq[1] = Bi; gq[2] = Gj; gq[3] = Bj; gq[4] = Gf; gq[5] = Bf;
+        }
+        const bool hiq = (p & 1) != 0;
+        const float2 gi = hiq ? make_float2(gq[0].z, gq[0].w) : make_float2(gq[0].x, gq[0].y);
+        const float2 bi = hiq ? make_float2(gq[1].z, gq[1].w) : make_float2(gq[1].x, gq[1].y);
+        const float2 gj = hiq ? make_float2(gq[2].z, gq[2].w) : make_float2(gq[2].x, gq[2].y);
+        const float2 bj = hiq ? make_float2(gq[3].z, gq[3].w) : make_float2(gq[3].x, gq[3].y);
+        const float2 gf = hiq ? make_float2(gq[4].z, gq[4].w) : make_float2(gq[4].x, gq[4].y);
+        const float2 bf = hiq ? make_float2(gq[5].z, gq[5].w) : make_float2(gq[5].x, gq[5].y);
         const float2 in = __ffma2_rn(__ffma2_rn(make_float2(vi[2 * p], vi[2 * p + 1]), make_float2(rs0, rs0),
-                                                make_float2(mu0, mu0)), gi[p], bi[p]);
+                                                make_float2(mu0, mu0)), gi, bi);
         const float2 jn = __ffma2_rn(__ffma2_rn(make_float2(vj[2 * p], vj[2 * p + 1]), make_float2(rs1, rs1),
-                                                make_float2(mu1, mu1)), gj[p], bj[p]);
-        const float2 fn = __fadd2_rn(__ffma2_rn(__ffma2_rn(make_float2(vf[2 * p], vf[2 * p + 1]), make_float2(rs2, rs2),
-                                                           make_float2(mu2, mu2)), gf[p], bf[p]),
-                                     make_float2(FORGET_BIAS, FORGET_BIAS));
+                                                make_float2(mu1, mu1)), gj, bj);
+        const float2 fn = __ffma2_rn(__ffma2_rn(make_float2(vf[2 * p], vf[2 * p + 1]), make_float2(rs2, rs2),
+                                                make_float2(mu2, mu2)), gf, bf);
         const float4 c4 = cur[p >> 1];
         const float2 cold = (p & 1) ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
-        const float2 cn2 = __ffma2_rn(cold, ptx::sigmoid2(fn), __fmul2_rn(ptx::sigmoid2(in), ptx::relu2(jn)));
+        // c*sigmoid(f) + sigmoid(i)*relu(j) = (c*Q + relu(j)*P) / (P*Q), P = 1+e^-f, Q = 1+e^-i:
+        // one reciprocal for the two logistic functions
+        const float2 P = one_plus_ex2(fn), Q = one_plus_ex2(in);   // in / fn are already -x log2 e
+        const float2 den = __fmul2_rn(P, Q);
+        const float2 num = __ffma2_rn(cold, Q, __fmul2_rn(ptx::relu2(jn), P));
+        const float2 cn2 = __fmul2_rn(num, make_float2(ptx::rcp_approx(den.x), ptx::rcp_approx(den.y)));
         cnew[2 * p] = cn2.x;
         cnew[2 * p + 1] = cn2.y;
       }
       ptx::tmem_st16(t_acc + cc * 16, cnew);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+      for (int q = 0; q < 4; ++q) {
+        cur[q] = nx1[q];
+        nx1[q] = nx2[q];
+      }
     }
+    tl_mark(tl, e, n, 3);
     float crs, cm;
     row_stats64(t_acc, crs, cm);
+    tl_mark(tl, e, n, 4);
     // ---- LayerNorm of the cell state, output gate, new h; straight to global memory -------------
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
@@ -355,19 +429,29 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[e]);
       }
-      const float2* go = reinterpret_cast<const float2*>(ln.gamma[3] + cc * 16);
-      const float2* bo = reinterpret_cast<const float2*>(ln.beta[3] + cc * 16);
-      const float2* gs = reinterpret_cast<const float2*>(ln.gamma[4] + cc * 16);
-      const float2* bs = reinterpret_cast<const float2*>(ln.beta[4] + cc * 16);
+      const uint32_t lcc = ln_s + cc * 64;
       float2 c2[8];
       uint32_t hi[8], lo[8];
+      float4 gq[4];
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
+        if ((p & 1) == 0) {
+          gq[0] = ptx::lds128f(lcc + 3 * 256 + (p >> 1) * 16);
+          gq[1] = ptx::lds128f(lcc + 1280 + 3 * 256 + (p >> 1) * 16);
+          gq[2] = ptx::lds128f(lcc + 4 * 256 + (p >> 1) * 16);
+          gq[3] = ptx::lds128f(lcc + 1280 + 4 * 256 + (p >> 1) * 16);
+        }
+        const bool hiq = (p & 1) != 0;
+        const float2 go = hiq ? make_float2(gq[0].z, gq[0].w) : make_float2(gq[0].x, gq[0].y);
+        const float2 bo = hiq ? make_float2(gq[1].z, gq[1].w) : make_float2(gq[1].x, gq[1].y);
+        const float2 gs = hiq ? make_float2(gq[2].z, gq[2].w) : make_float2(gq[2].x, gq[2].y);
+        const float2 bs = hiq ? make_float2(gq[3].z, gq[3].w) : make_float2(gq[3].x, gq[3].y);
         const float2 on = __ffma2_rn(__ffma2_rn(make_float2(vo[2 * p], vo[2 * p + 1]), make_float2(rs3, rs3),
-                                                make_float2(mu3, mu3)), go[p], bo[p]);
+                                                make_float2(mu3, mu3)), go, bo);
         c2[p] = __ffma2_rn(__ffma2_rn(make_float2(cs[2 * p], cs[2 * p + 1]), make_float2(crs, crs),
-                                      make_float2(cm, cm)), gs[p], bs[p]);
-        const float2 hn = __fmul2_rn(ptx::relu2(c2[p]), ptx::sigmoid2(on));
+                                      make_float2(cm, cm)), gs, bs);
+        const float2 eo = one_plus_ex2(on);                         // on is already -x log2 e
+        const float2 hn = __fmul2_rn(ptx::relu2(c2[p]), make_float2(ptx::rcp_approx(eo.x), ptx::rcp_approx(eo.y)));
         ptx::split_bf16x2_p(hn, hi[p], lo[p]);
       }
 #pragma unroll
@@ -379,6 +463,7 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
         if (HP == 2) hg[1024 + (cc * 2 + q) * 128] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
       }
     }
+    tl_mark(tl, e, n, 5);
   }
 }
 
@@ -417,20 +502,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
     ptx::fence_mbar_init();
   }
   if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
+  {
+    // LayerNorm parameters of this CTA's cell.  The three gates that only feed a logistic function
+    // (input 0, forget 2, output 3) are stored pre-multiplied by -log2(e), with the forget bias
+    // folded into beta: the epilogue then gets the exponent of 2^(-x log2 e) straight from the FMA.
+    float* ln_sm = reinterpret_cast<float*>(smem + L::LN_OFF);
+    const CellLN& ln = c_ln[is_v ? 0 : 1];
+    constexpr float NL2E = -1.4426950408889634f;
+    for (int i = tid; i < 5 * D; i += TC_THREADS) {
+      const int g = i >> 6;
+      const bool sig = (g == 0) || (g == 2) || (g == 3);
+      const float gam = ln.gamma[g][i & 63], bet = ln.beta[g][i & 63] + (g == 2 ? FORGET_BIAS : 0.f);
+      ln_sm[i] = sig ? gam * NL2E : gam;
+      ln_sm[5 * D + i] = sig ? bet * NL2E : bet;
+    }
+  }
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t ln_s = ptx::smem_u32(smem + L::LN_OFF);
 
   if (warp < 8) {
     ptx::setmaxnreg_inc<200>();   // ... 256 x (200 - 168) = 8192 taken by the two epilogue warpgroups
-    if (is_v) k1_epilogue<HP, 0>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane);
-    else k1_epilogue<HP, 1>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane);
+    if (is_v) k1_epilogue<HP, 0>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+    else k1_epilogue<HP, 1>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
   } else {
     ptx::setmaxnreg_dec<104>();   // 128 x (168 - 104) = 8192 registers back to the CTA pool ...
     if (warp == 8) {
-      if (lane == 0 && ntiles > 0)
-        k1_mma<HP>(is_v ? a.wV : a.wE, wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles);
+      if (ntiles > 0)
+        k1_mma<HP>(is_v ? a.wV : a.wE, wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles, a.timeline);
     } else {
       if (is_v) k1_producer<HP, true>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
       else k1_producer<HP, false>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
@@ -454,9 +555,11 @@ struct K2Smem {
   static constexpr int P_OFF = IN_OFF + NIN * IN_BYTES;
   static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;
   static constexpr int NBAR = 1 + 2 * NIN + 4;
-  static constexpr int TOTAL = BAR_OFF + 8 * NBAR + 16;
+  static constexpr int BIAS_OFF = (BAR_OFF + 8 * NBAR + 16 + 15) & ~15;   // b[4][64] of this CTA's MLP
+  static constexpr int TOTAL = BIAS_OFF + 4 * D * 4;
   static constexpr int DYN_BYTES = TOTAL + 128;
 };
+static_assert(K2Smem<2>::DYN_BYTES <= 232448, "K2 shared memory budget (227 KB)");
 
 // fp32 staging of a 128 x 64 message tile: 256-B rows, 16-B chunk index XOR (row & 7)
 __device__ __forceinline__ uint32_t stage_off(int r, int chunk) {
@@ -467,119 +570,140 @@ __device__ __forceinline__ uint32_t stage_off(int r, int chunk) {
 // ROLE 0 = V rows (V_msg_E, message stored), 1 = E rows (E_msg_V, scatter-add), 2 = E rows vote
 template <int HP, int ROLE>
 __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint8_t* pbuf, uint64_t* acc_full,
-                                         uint64_t* act_ready, uint32_t tmem, int t0, int ntiles, int warp, int lane) {
+                                         uint64_t* act_ready, uint32_t tmem, int t0, int ntiles, int warp, int lane,
+                                         uint32_t bias_s) {
   using L = K2Smem<HP>;
   constexpr int NL = (ROLE == 2) ? 3 : 4;
   const int e = warp >> 2, q4 = warp & 3;
   const int r = q4 * 32 + lane;
   const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 64;
-  const MlpBias& bias = c_mlp_bias[ROLE == 2 ? 2 : ROLE];
   const int64_t n_rows = (ROLE == 0) ? a.nV : a.nE;
+  long long* tl = (q4 == 0 && lane == 0) ? a.timeline : nullptr;
+  const uint32_t p_s = ptx::smem_u32(pbuf), in_s = ptx::smem_u32(in_bufs);
   uint32_t step = 0;
   for (int n = e; n < ntiles; n += 2) {
     const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
-    uint8_t* ibuf = in_bufs + (n % L::NIN) * L::IN_BYTES;
+    const uint32_t i_s = in_s + (n % L::NIN) * L::IN_BYTES;
     float v[64];
 #pragma unroll 1
     for (int l = 0; l < NL; ++l, ++step) {
       ptx::mbar_wait(&acc_full[e], step & 1);
+      tl_mark(tl, e, n, l);
       ptx::tcgen05_fence_after();
       ptx::tmem_ld64(t_acc, v);
       const bool hidden = (ROLE == 2) || (l < 3);
       const bool feeds_mma = l < NL - 1;
       if (hidden) {
-        uint8_t* nxt = (l & 1) ? ibuf : pbuf;     // layer l reads (l even ? in : pong), writes the other
-        const float2* b2 = reinterpret_cast<const float2*>(bias.b[l]);
+        const uint32_t nxt = ((l & 1) ? i_s : p_s) + r * 16;   // layer l reads (l even ? in : pong), writes the other
+        const uint32_t bl = bias_s + l * 256;       // broadcast LDS.128: four bias values per load
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           uint32_t hi[4], lo[4];
+          const float4 ba = ptx::lds128f(bl + ch * 32), bb = ptx::lds128f(bl + ch * 32 + 16);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const int j = ch * 8 + 2 * p;
-            const float2 x = ptx::relu2(__fadd2_rn(make_float2(v[j], v[j + 1]), b2[ch * 4 + p]));
+            const float2 bp = (p == 0) ? make_float2(ba.x, ba.y) : (p == 1) ? make_float2(ba.z, ba.w)
+                            : (p == 2) ? make_float2(bb.x, bb.y) : make_float2(bb.z, bb.w);
+            const float2 x = ptx::relu2(__fadd2_rn(make_float2(v[j], v[j + 1]), bp));
             v[j] = x.x;
             v[j + 1] = x.y;
             ptx::split_bf16x2_p(x, hi[p], lo[p]);
           }
           if (feeds_mma) {
-            const uint32_t off = ch * 2048 + r * 16;
-            *reinterpret_cast<uint4*>(nxt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (HP == 2) *reinterpret_cast<uint4*>(nxt + PLANE_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            ptx::sts128(nxt + ch * 2048, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            if (HP == 2) ptx::sts128(nxt + PLANE_BYTES + ch * 2048, make_uint4(lo[0], lo[1], lo[2], lo[3]));
           }
         }
         if (feeds_mma) ptx::fence_proxy_async_smem();
       }
       ptx::tcgen05_fence_before();
-      ptx::mbar_arrive(&act_ready[e]);            // activations written / accumulator drained
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&act_ready[e]);   // activations written / accumulator drained
     }
-    const int64_t grow = row0 + r;
+    tl_mark(tl, e, n, 4);
     if (ROLE == 2) {
       // 64 -> 1 tail of E_vote on the fp32 layer-3 activations (model.py:107-128)
+      const int64_t grow = row0 + r;
       float s = c_vote_tail.b4;
 #pragma unroll
       for (int j = 0; j < 64; ++j) s = fmaf(v[j], c_vote_tail.w4[j], s);
       if (grow < n_rows) a.vote[grow] = s;
     } else {
-      // stage the fp32 messages; each warp then walks its own 32 rows with row-wide accesses
-      float* stage = reinterpret_cast<float*>(pbuf);
+      // stage the fp32 messages; each warp then walks its own 32 rows, two rows per instruction
+      // (a half-warp covers the 256 bytes of a row with 16-byte accesses)
 #pragma unroll
-      for (int q = 0; q < 16; ++q)
-        *reinterpret_cast<float4*>(pbuf + stage_off(r, q)) =
-            make_float4(v[4 * q] + bias.b[3][4 * q], v[4 * q + 1] + bias.b[3][4 * q + 1],
-                        v[4 * q + 2] + bias.b[3][4 * q + 2], v[4 * q + 3] + bias.b[3][4 * q + 3]);
+      for (int q = 0; q < 16; ++q) {
+        const float4 bb = ptx::lds128f(bias_s + 3 * 256 + q * 16);
+        ptx::sts128f(p_s + stage_off(r, q),
+                     make_float4(v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w));
+      }
       __syncwarp();
       const int64_t g0 = row0 + q4 * 32;
+      const int hw = lane >> 4, c16 = lane & 15;
       if (ROLE == 0) {
-        for (int rr = 0; rr < 32; ++rr) {
-          if (g0 + rr >= n_rows) break;
-          const int row = q4 * 32 + rr;
-          const float2 m = *reinterpret_cast<const float2*>(pbuf + stage_off(row, lane >> 1) + (lane & 1) * 8);
-          *reinterpret_cast<float2*>(a.mV + (g0 + rr) * D + 2 * lane) = m;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int rr = 2 * i + hw;
+          if (g0 + rr < n_rows) {
+            const float4 m = ptx::lds128f(p_s + stage_off(q4 * 32 + rr, c16));
+            *reinterpret_cast<float4*>(a.mV + (g0 + rr) * D + 4 * c16) = m;
+          }
         }
       } else {
         // dst side: one vector reduction per row; src side accumulated over runs of equal src
         // (rows of a complete graph are sorted by src, instance_loader.py:60)
         int my_s = -1, my_d = -1;
         if (g0 + lane < n_rows) {
-          my_s = a.src[g0 + lane];
-          my_d = a.dst[g0 + lane];
+          my_s = __ldg(a.src + g0 + lane);
+          my_d = __ldg(a.dst + g0 + lane);
         }
         int cur_s = -1;
-        float2 acc = make_float2(0.f, 0.f);
-        for (int rr = 0; rr < 32; ++rr) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int rr = 2 * i + hw;
           const int s = __shfl_sync(0xffffffffu, my_s, rr);
           const int d = __shfl_sync(0xffffffffu, my_d, rr);
-          if (s < 0) break;
-          const int row = q4 * 32 + rr;
-          const float2 m = *reinterpret_cast<const float2*>(pbuf + stage_off(row, lane >> 1) + (lane & 1) * 8);
-          ptx::red_add_v2(a.xV + static_cast<int64_t>(d) * D + 2 * lane, m.x, m.y);
-          if (s != cur_s) {
-            if (cur_s >= 0) ptx::red_add_v2(a.xV + static_cast<int64_t>(cur_s) * D + 2 * lane, acc.x, acc.y);
-            cur_s = s;
-            acc = m;
-          } else {
-            acc.x += m.x;
-            acc.y += m.y;
+          if (s >= 0) {
+            const float4 m = ptx::lds128f(p_s + stage_off(q4 * 32 + rr, c16));
+            ptx::red_add_v4(a.xV + static_cast<int64_t>(d) * D + 4 * c16, m);
+            if (s != cur_s) {
+              if (cur_s >= 0) ptx::red_add_v4(a.xV + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
+              cur_s = s;
+              acc = m;
+            } else {
+              acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+            }
           }
         }
-        if (cur_s >= 0) ptx::red_add_v2(a.xV + static_cast<int64_t>(cur_s) * D + 2 * lane, acc.x, acc.y);
+        if (cur_s >= 0) ptx::red_add_v4(a.xV + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
       }
-      (void)stage;
       // the pong buffer is rewritten (in the operand layout) by this warpgroup's next tile
       asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
     }
+    tl_mark(tl, e, n, 5);
   }
 }
 
+// Executed by the whole warp (converged); one elected lane issues the tcgen05 instructions.
 template <int HP>
 __device__ __forceinline__ void k2_mma(const uint8_t* wimg, uint8_t* wsm, uint8_t* in_bufs, uint8_t* pbufs,
                                        uint64_t* bar_w, uint64_t* in_full, uint64_t* in_free, uint64_t* acc_full,
-                                       uint64_t* act_ready, uint32_t tmem, int ntiles, int n_layers) {
+                                       uint64_t* act_ready, uint32_t tmem, int ntiles, int n_layers, long long* tl_) {
   using L = K2Smem<HP>;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 64);
-  ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-  for (int off = 0; off < L::W_BYTES; off += 16384) ptx::bulk_g2s(wsm + off, wimg + off, 16384, bar_w);
+  const bool leader = ptx::elect_one();
+  long long* tl = leader ? tl_ : nullptr;
+  if (leader) {
+    ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+    for (int off = 0; off < L::W_BYTES; off += 16384) ptx::bulk_g2s(wsm + off, wimg + off, 16384, bar_w);
+  }
+  __syncwarp();
   ptx::mbar_wait(bar_w, 0);
+  const uint64_t idesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(in_bufs), 2048, 128);
+  const uint64_t pdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(pbufs), 2048, 128);
+  const uint64_t bdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(wsm), 1024, 128);
   const int npairs = (ntiles + 1) >> 1;
   for (int pi = 0; pi < npairs; ++pi) {
     for (int l = 0; l < n_layers; ++l) {
@@ -592,24 +716,25 @@ __device__ __forceinline__ void k2_mma(const uint8_t* wimg, uint8_t* wsm, uint8_
         if (l == 0) ptx::mbar_wait(&in_full[slot], (n / L::NIN) & 1);
         if (step > 0) ptx::mbar_wait(&act_ready[e], (step - 1) & 1);
         ptx::tcgen05_fence_after();
-        const uint8_t* abuf = (l & 1) ? (pbufs + e * L::P_BYTES) : (in_bufs + slot * L::IN_BYTES);
-        uint32_t accumulate = 0;
-        constexpr int NCOMB = (HP == 2) ? 3 : 1;
-        const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
+        if (ptx::elect_one()) {
+          const uint64_t adesc = (l & 1) ? pdesc0 + static_cast<uint32_t>((e * L::P_BYTES) >> 4)
+                                         : idesc0 + static_cast<uint32_t>((slot * L::IN_BYTES) >> 4);
+          const uint64_t bdesc = bdesc0 + static_cast<uint32_t>((l * HP * 8192) >> 4);
+          constexpr int NCOMB = (HP == 2) ? 3 : 1;
+          const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
 #pragma unroll
-        for (int cb = 0; cb < NCOMB; ++cb) {
-          const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
-          const uint32_t abase = ptx::smem_u32(abuf + pa * PLANE_BYTES);
-          const uint32_t bbase = ptx::smem_u32(wsm + (l * HP + pb) * 8192);
+          for (int cb = 0; cb < NCOMB; ++cb) {
+            const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ptx::umma_bf16_ss(tmem + e * 64, ptx::umma_desc_k_nosw(abase + k * 4096, 2048, 128),
-                              ptx::umma_desc_k_nosw(bbase + k * 2048, 1024, 128), IDESC, accumulate);
-            accumulate = 1;
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_ss(tmem + e * 64, adesc + ((pa * PLANE_BYTES + k * 4096) >> 4),
+                                bdesc + ((pb * 8192 + k * 2048) >> 4), IDESC, (cb | k) ? 1u : 0u);
           }
+          ptx::umma_commit(&acc_full[e]);
+          if (l == 2) ptx::umma_commit(&in_free[slot]);   // last layer that reads the input slot
         }
-        ptx::umma_commit(&acc_full[e]);
-        if (l == 2) ptx::umma_commit(&in_free[slot]);   // last layer that reads the input slot
+        __syncwarp();
+        tl_mark(tl, 2, n, l);
       }
     }
   }
@@ -646,25 +771,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&act_ready[s], 128);
+      ptx::mbar_init(&act_ready[s], 4);
     }
     ptx::fence_mbar_init();
   }
   if (warp == 8) ptx::tmem_alloc(tmem_slot, 128);
+  {
+    float* bias_sm = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+    const MlpBias& bias = c_mlp_bias[a.vote_mode ? 2 : (is_v ? 0 : 1)];
+    for (int i = tid; i < 4 * D; i += TC_THREADS) bias_sm[i] = bias.b[i >> 6][i & 63];
+  }
   ptx::tcgen05_fence_before();
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t bias_s = ptx::smem_u32(smem + L::BIAS_OFF);
 
   if (warp < 8) {
     uint8_t* pbuf = pbufs + (warp >> 2) * L::P_BYTES;
-    if (a.vote_mode) k2_chain<HP, 2>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane);
-    else if (is_v) k2_chain<HP, 0>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane);
-    else k2_chain<HP, 1>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane);
+    if (a.vote_mode) k2_chain<HP, 2>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane, bias_s);
+    else if (is_v) k2_chain<HP, 0>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane, bias_s);
+    else k2_chain<HP, 1>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane, bias_s);
   } else if (warp == 8) {
-    if (lane == 0 && ntiles > 0)
+    if (ntiles > 0)
       k2_mma<HP>(is_v ? a.wV : a.wE, wsm, in_bufs, pbufs, bar_w, in_full, in_free, acc_full, act_ready, tmem, ntiles,
-                 a.vote_mode ? 3 : 4);
+                 a.vote_mode ? 3 : 4, a.timeline);
   } else if (warp == 9) {
     if (lane == 0) {
       for (int n = 0; n < ntiles; ++n) {

@@ -438,8 +438,9 @@ static void role_split(const tspgnn_ctx* h, int tilesE, int tilesV, int& grid, i
 }
 
 template <int HP>
-static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote) {
+static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, long long* timeline = nullptr) {
   K2Args a;
+  a.timeline = timeline;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = vote ? h->d_wmlp[2] : h->d_wmlp[1];
@@ -462,8 +463,9 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote) {
 }
 
 template <int HP>
-static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s) {
+static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, long long* timeline = nullptr) {
   K1Args a;
+  a.timeline = timeline;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = h->d_wlstm[1];
@@ -732,6 +734,36 @@ extern "C" int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* 
   cudaEventDestroy(e1);
   *mean_ms = static_cast<float>(total / iters);
   return 0;
+}
+
+// Development aid (tools/timeline.py): one launch of K2 (which = 1) or K1 (which = 0) with the
+// clock64() trace enabled; out[cta][role][tile][event], n_int64 must cover grid * 4 * 64 * 8.
+extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_host, int64_t n_int64, void* stream) {
+  if (check_ready(h)) return TSPGNN_E_STATE;
+  if (h->hp == 0) return fail(TSPGNN_E_UNSUPPORTED, "timeline needs a tensor-core mode");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (upload_constants(h, s)) return TSPGNN_E_CUDA;
+  const int64_t need = static_cast<int64_t>(h->num_sms) * TL_ROLES * TL_TILES * TL_EVENTS;
+  if (!out_host || n_int64 < need) return fail(TSPGNN_E_INVALID, "timeline buffer needs %lld int64", (long long)need);
+  long long* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, need * 8));
+  CUDA_TRY(cudaMemsetAsync(d, 0, need * 8, s));
+  int rc;
+  if (which == 0) {
+    rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false) : tc_launch_k2<1>(h, s, false);
+    if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, d) : tc_launch_k1<1>(h, s, d);
+  } else {
+    rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, d) : tc_launch_k2<1>(h, s, false, d);
+    if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s) : tc_launch_k1<1>(h, s);
+  }
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out_host, d, need * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(TSPGNN_E_CUDA, "timeline copy failed: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------
