@@ -202,3 +202,19 @@ def test_replanning_and_repeatability(mode):
         assert np.abs(again - outs[-1]).max() <= 2e-6      # atomics may reorder fp32 sums
     eng.close()
     assert np.abs(outs[0] - outs[2]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("mode", ["simt", "bf16x3"])
+def test_cuda_path_matches_reference_graph_code_fixtures(mode):
+    """Predictions of the CUDA path against the outputs of the reference's own model.py / graphnn.py /
+    mlp.py executed on the numpy TF1 stand-in (tests/golden/make_reference_golden.py)."""
+    import make_reference_golden as mrg
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_shim_forward.npz"))
+    for name in sorted(mrg.CASES):
+        sizes, iseed, pseed, T, conn = mrg.CASES[name]
+        EV, W, C, y, nv, ne = inst.synth_batch(sizes, seed=iseed, connectivity=conn)
+        params = orc.init_params(64, seed=pseed, perturb_ln=True)
+        got = run_engine(mode, params, EV, W, C, nv, ne, T)
+        assert np.abs(got["predictions"] - gold[name + "/predictions"]).max() <= TOL_PRED[mode]
+        assert state_err(got["V_h"], gold[name + "/V_h"]) <= TOL_STATE[mode]
+        assert state_err(got["E_c"][:48], gold[name + "/E_c_head"]) <= TOL_STATE[mode]
