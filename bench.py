@@ -48,18 +48,19 @@ def algorithmic_bytes(nE, nV, state_bytes=4):
 
 
 class ClockSampler(object):
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line): started ahead of the
+    region, samples are kept if their timestamp falls inside [t0, t1] (host clock)."""
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.thr = index, [], None, None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -68,29 +69,38 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.02)
+
+    def stop(self, t0, t1):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
         self.thr.join(timeout=2)
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1 + 0.03:
+                continue
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                smax = float(f[1])
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
 def make_workload(rank):
@@ -191,7 +201,9 @@ def run_ours(args):
     stream.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_first_sample()
     barrier()
+    t_clock0 = time.time()
     launches0 = eng.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
@@ -205,7 +217,7 @@ def run_ours(args):
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launch_count - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_clock0, time.time())
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -292,7 +304,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "simt"])
