@@ -124,15 +124,15 @@ def cpu_loop_timesteps_per_s(params, EV, W, C, nv, ne, n_instances, timesteps, r
     V_h = np.tile(P32["V_init"] / np.sqrt(np.float32(D)), (nV, 1)).astype(np.float32)
     E_c, V_c = np.zeros_like(E_h), np.zeros_like(V_h)
     best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        orc.message_passing(P32, src, dst, dense, E_c, E_h, V_c, V_h, timesteps)
-        best = min(best, time.perf_counter() - t0)
-    try:
-        from threadpoolctl import threadpool_info
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    from threadpoolctl import threadpool_info, threadpool_limits
+    # every host core, also under torchrun (which exports OMP_NUM_THREADS=1)
+    with threadpool_limits(limits=ncpu):
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            orc.message_passing(P32, src, dst, dense, E_c, E_h, V_c, V_h, timesteps)
+            best = min(best, time.perf_counter() - t0)
         threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        threads = os.cpu_count() or 1
     return timesteps / best, best, threads
 
 
