@@ -232,19 +232,14 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
 // ---- MMA issuer: z[128 x 256] = [x,h] . K, accumulators alternate between two TMEM halves ----
 // Executed by the whole warp (converged); one elected lane issues the tcgen05 instructions.
 template <int HP>
-__device__ __forceinline__ void k1_mma(const uint8_t* wimg, uint8_t* wsm, uint8_t* ring, uint64_t* bar_w,
+__device__ __forceinline__ void k1_mma(uint8_t* wsm, uint8_t* ring, uint64_t* bar_w,
                                        uint64_t* full, uint64_t* empty, uint64_t* acc_full, uint64_t* acc_empty,
                                        uint32_t tmem, int ntiles, long long* tl_) {
   using L = K1Smem<HP>;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 256);
   const bool leader = ptx::elect_one();
   long long* tl = leader ? tl_ : nullptr;
-  if (leader) {
-    ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-    for (int off = 0; off < L::W_BYTES; off += 32768) ptx::bulk_g2s(wsm + off, wimg + off, 32768, bar_w);
-  }
-  __syncwarp();
-  ptx::mbar_wait(bar_w, 0);
+  ptx::mbar_wait(bar_w, 0);          // weight images (staged by the kernel prologue)
   // descriptors of the first k-step of (ring slot 0, plane 0) and of (weight plane 0, k-block 0);
   // everything else is an offset in 16-byte units added to the low word
   const uint64_t adesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(ring), 2048, 128);
@@ -500,6 +495,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
       ptx::mbar_init(&acc_empty[s], 4);
     }
     ptx::fence_mbar_init();
+    if (ntiles > 0) {   // weight images: parameters, not produced by the preceding kernel
+      const uint8_t* wimg = is_v ? a.wV : a.wE;
+      ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+      for (int off = 0; off < L::W_BYTES; off += 32768) ptx::bulk_g2s(wsm + off, wimg + off, 32768, bar_w);
+    }
   }
   if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
   {
@@ -522,6 +522,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
   ptx::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t ln_s = ptx::smem_u32(smem + L::LN_OFF);
+  // everything above overlapped the tail of the previous kernel (programmatic dependent launch);
+  // from here on the recurrent state and the messages it produced are read
+  ptx::grid_dependency_wait();
+  ptx::grid_launch_dependents();
 
   if (warp < 8) {
     ptx::setmaxnreg_inc<200>();   // ... 256 x (200 - 168) = 8192 taken by the two epilogue warpgroups
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
     ptx::setmaxnreg_dec<104>();   // 128 x (168 - 104) = 8192 registers back to the CTA pool ...
     if (warp == 8) {
       if (ntiles > 0)
-        k1_mma<HP>(is_v ? a.wV : a.wE, wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles, a.timeline);
+        k1_mma<HP>(wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles, a.timeline);
     } else {
       if (is_v) k1_producer<HP, true>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
       else k1_producer<HP, false>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
@@ -688,19 +692,14 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
 
 // Executed by the whole warp (converged); one elected lane issues the tcgen05 instructions.
 template <int HP>
-__device__ __forceinline__ void k2_mma(const uint8_t* wimg, uint8_t* wsm, uint8_t* in_bufs, uint8_t* pbufs,
+__device__ __forceinline__ void k2_mma(uint8_t* wsm, uint8_t* in_bufs, uint8_t* pbufs,
                                        uint64_t* bar_w, uint64_t* in_full, uint64_t* in_free, uint64_t* acc_full,
                                        uint64_t* act_ready, uint32_t tmem, int ntiles, int n_layers, long long* tl_) {
   using L = K2Smem<HP>;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 64);
   const bool leader = ptx::elect_one();
   long long* tl = leader ? tl_ : nullptr;
-  if (leader) {
-    ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
-    for (int off = 0; off < L::W_BYTES; off += 16384) ptx::bulk_g2s(wsm + off, wimg + off, 16384, bar_w);
-  }
-  __syncwarp();
-  ptx::mbar_wait(bar_w, 0);
+  ptx::mbar_wait(bar_w, 0);          // weight images (staged by the kernel prologue)
   const uint64_t idesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(in_bufs), 2048, 128);
   const uint64_t pdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(pbufs), 2048, 128);
   const uint64_t bdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(wsm), 1024, 128);
@@ -774,6 +773,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
       ptx::mbar_init(&act_ready[s], 4);
     }
     ptx::fence_mbar_init();
+    if (ntiles > 0) {   // weight images: parameters, not produced by the preceding kernel
+      const uint8_t* wimg = is_v ? a.wV : a.wE;
+      ptx::mbar_arrive_expect_tx(bar_w, L::W_BYTES);
+      for (int off = 0; off < L::W_BYTES; off += 16384) ptx::bulk_g2s(wsm + off, wimg + off, 16384, bar_w);
+    }
   }
   if (warp == 8) ptx::tmem_alloc(tmem_slot, 128);
   {
@@ -786,6 +790,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   ptx::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t bias_s = ptx::smem_u32(smem + L::BIAS_OFF);
+  ptx::grid_dependency_wait();       // prologue above overlaps the previous kernel's tail
+  ptx::grid_launch_dependents();
 
   if (warp < 8) {
     uint8_t* pbuf = pbufs + (warp >> 2) * L::P_BYTES;
@@ -794,7 +800,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
     else k2_chain<HP, 1>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane, bias_s);
   } else if (warp == 8) {
     if (ntiles > 0)
-      k2_mma<HP>(is_v ? a.wV : a.wE, wsm, in_bufs, pbufs, bar_w, in_full, in_free, acc_full, act_ready, tmem, ntiles,
+      k2_mma<HP>(wsm, in_bufs, pbufs, bar_w, in_full, in_free, acc_full, act_ready, tmem, ntiles,
                  a.vote_mode ? 3 : 4, a.timeline);
   } else if (warp == 9) {
     if (lane == 0) {

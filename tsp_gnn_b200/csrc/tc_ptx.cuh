@@ -310,6 +310,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
+// ------------------------------- programmatic dependent launch -------------------------
+// wait: blocks until the grids this one depends on have completed and flushed their memory;
+// everything before it (barrier init, TMEM allocation, weight staging) overlaps their tail.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------- misc ----------------------------------------------
 // xV[v] += {a, b}: vector reduction to global memory (sm_90+)
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {

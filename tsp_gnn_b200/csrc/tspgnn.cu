@@ -420,16 +420,35 @@ static int check_ready(tspgnn_ctx* h) {
       return fail(TSPGNN_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// Launch with programmatic stream serialization: the kernel may start (and run its prologue up to
+// griddepcontrol.wait) while the preceding kernel of the stream is still draining.
+template <typename Args>
+static cudaError_t launch_pdl(void (*kernel)(const Args), int grid, int smem, cudaStream_t s, const Args& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 static inline int grid_for(int64_t n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
 
-static void role_split(const tspgnn_ctx* h, int tilesE, int tilesV, int& grid, int& e_ctas) {
+// CTAs are dedicated to edge tiles or to vertex tiles; `v_weight` is the measured cost of a vertex
+// tile relative to an edge tile (K1: the read-and-clear of xV makes its producer slower; K2: no scatter).
+static void role_split(const tspgnn_ctx* h, int tilesE, int tilesV, double v_weight, int& grid, int& e_ctas) {
   const int total = tilesE + tilesV;
   grid = std::min(h->num_sms, total);
   if (tilesV == 0) {
     e_ctas = grid;
     return;
   }
-  e_ctas = static_cast<int>(std::lround(static_cast<double>(grid) * tilesE / total));
+  e_ctas = static_cast<int>(std::lround(static_cast<double>(grid) * tilesE / (tilesE + v_weight * tilesV)));
   e_ctas = std::max(1, std::min(e_ctas, grid - 1));
   if (grid < 2) {   // one SM-sized job: still needs both roles
     grid = 2;
@@ -456,8 +475,8 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, long long* tim
   a.tilesV = vote ? 0 : h->tilesV;
   a.vote_mode = vote ? 1 : 0;
   int grid;
-  role_split(h, a.tilesE, a.tilesV, grid, a.e_ctas);
-  tc_mlp_kernel<HP><<<grid, TC_THREADS, K2Smem<HP>::DYN_BYTES, s>>>(a);
+  role_split(h, a.tilesE, a.tilesV, 0.8, grid, a.e_ctas);
+  CUDA_TRY(launch_pdl(tc_mlp_kernel<HP>, grid, K2Smem<HP>::DYN_BYTES, s, a));
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -479,8 +498,8 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, long long* timeline = nul
   a.tilesE = h->tilesE;
   a.tilesV = h->tilesV;
   int grid;
-  role_split(h, a.tilesE, a.tilesV, grid, a.e_ctas);
-  tc_lnlstm_kernel<HP><<<grid, TC_THREADS, K1Smem<HP>::DYN_BYTES, s>>>(a);
+  role_split(h, a.tilesE, a.tilesV, 1.35, grid, a.e_ctas);
+  CUDA_TRY(launch_pdl(tc_lnlstm_kernel<HP>, grid, K1Smem<HP>::DYN_BYTES, s, a));
   LAUNCH_CHECK(h);
   return 0;
 }
