@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(512, 1) tput_kernel(int iters, long long* out,
   for (int k = 0; k < 8; ++k) x[k] = make_float2(0.001f * (threadIdx.x + k), 1.0f + 0.002f * k);
   uint32_t u[8];
   for (int k = 0; k < 8; ++k) u[k] = threadIdx.x * 7 + k;
+  float2 y[8], z[8];
+  for (int k = 0; k < 8; ++k) { y[k] = make_float2(1.0f + 0.001f * k, 0.5f); z[k] = make_float2(0.9f, 1.0f - 0.001f * k); }
   __shared__ float4 sm[512];
   __syncthreads();
   const long long t0 = clock64();
@@ -40,6 +42,20 @@ __global__ void __launch_bounds__(512, 1) tput_kernel(int iters, long long* out,
       } else if (KIND == 6) {   // LDS.128 broadcast (all lanes same address)
         const float4 g = sm[(idx + k) & 511];
         x[k] = __ffma2_rn(x[k], make_float2(g.x, g.y), make_float2(g.z, g.w));
+      } else if (KIND == 8) {   // MUFU.EX2 and two independent FFMA2 per slot (do the pipes overlap?)
+        x[k].x = ptx::ex2_approx(x[k].x);
+        y[k] = __ffma2_rn(y[k], y[(k + 1) & 7], y[(k + 2) & 7]);
+        z[k] = __ffma2_rn(z[k], z[(k + 1) & 7], z[(k + 2) & 7]);
+      } else if (KIND == 9) {   // MUFU.EX2 + 4 scalar FMNMX (alu pipe)
+        x[k].x = ptx::ex2_approx(x[k].x);
+        y[k].x = fmaxf(y[k].x, y[(k + 1) & 7].y);
+        y[k].y = fminf(y[k].y, y[(k + 3) & 7].x);
+        z[k].x = fmaxf(z[k].x, z[(k + 1) & 7].y);
+        z[k].y = fminf(z[k].y, z[(k + 3) & 7].x);
+      } else if (KIND == 10) {  // FFMA2 + 2 FMNMX (fma pipe vs alu pipe)
+        y[k] = __ffma2_rn(y[k], y[(k + 1) & 7], y[(k + 2) & 7]);
+        z[k].x = fmaxf(z[k].x, z[(k + 1) & 7].y);
+        z[k].y = fminf(z[k].y, z[(k + 3) & 7].x);
       } else if (KIND == 7) {   // scalar FFMA with constant operand c[][] immediate address
         x[k].x = fmaf(x[k].x, c_tab[k], c_tab[k + 8]);
         x[k].y = fmaf(x[k].y, c_tab[k + 16], c_tab[k + 24]);
@@ -49,7 +65,7 @@ __global__ void __launch_bounds__(512, 1) tput_kernel(int iters, long long* out,
   const long long t1 = clock64();
   if (lane == 0) out[warp] = t1 - t0;
   float s = 0;
-  for (int k = 0; k < 8; ++k) s += x[k].x + x[k].y + u[k];
+  for (int k = 0; k < 8; ++k) s += x[k].x + x[k].y + u[k] + y[k].x + y[k].y + z[k].x + z[k].y;
   if (s == 123.456f) sink[0] = s + sm[0].x;
 }
 
@@ -80,5 +96,8 @@ int main() {
   run<5>("STS.128 + fence.proxy.async", d, sink, 8);
   run<6>("LDS.128 bcast + FFMA2", d, sink, 8);
   run<7>("FFMA x2 const-operand", d, sink, 16);
+  run<8>("slot: MUFU + 2 FFMA2", d, sink, 8);
+  run<9>("slot: MUFU + 4 FMNMX", d, sink, 8);
+  run<10>("slot: FFMA2 + 2 FMNMX", d, sink, 8);
   return 0;
 }

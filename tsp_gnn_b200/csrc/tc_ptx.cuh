@@ -277,6 +277,74 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       : "memory");
 }
 
+// ------------------------------- 16-lane TMEM accesses ---------------------------------
+// .16x256b.xN: one warp touches 16 lanes x 8N columns.  Thread t (t0 = t & 3, t1 = t >> 2) gets
+//   reg[4k + 2hi + j] = (lane base + t1 + 8*hi, column c0 + 8k + 2*t0 + j),  k < N, hi < 2, j < 2
+// (verified on B200 by tools/microbench/tmem_layout.cu, including a lane base of +16 inside the
+// warp's 32-lane sub-partition).  A row is spread over the 4 threads of a quad, so two warps can
+// share one 32-lane quarter and row reductions are two shuffles.
+__device__ __forceinline__ void tmem_ld_q8(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// three 16-column pieces (x2) in flight, one wait
+__device__ __forceinline__ void tmem_ld_q2x3(uint32_t a0, uint32_t a1, uint32_t a2, float (&v0)[8], float (&v1)[8],
+                                             float (&v2)[8]) {
+  uint32_t r[24];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+      : "r"(a0), "r"(a1), "r"(a2)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v0[i] = __uint_as_float(r[i]);
+    v1[i] = __uint_as_float(r[8 + i]);
+    v2[i] = __uint_as_float(r[16 + i]);
+  }
+}
+__device__ __forceinline__ void tmem_ld_q2x2(uint32_t a0, uint32_t a1, float (&v0)[8], float (&v1)[8]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(a0), "r"(a1)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v0[i] = __uint_as_float(r[i]);
+    v1[i] = __uint_as_float(r[8 + i]);
+  }
+}
+__device__ __forceinline__ void tmem_st_q2(uint32_t taddr, const float (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n\t"
+      "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+      : "memory");
+}
+
 // ------------------------------- register re-allocation ------------------------------
 // executed by every warp of a warpgroup (4 consecutive warps, first one a multiple of 4)
 template <int N>
@@ -298,6 +366,11 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
 __device__ __forceinline__ void sts128f(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+__device__ __forceinline__ float2 lds64f(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
 }
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   float4 v;

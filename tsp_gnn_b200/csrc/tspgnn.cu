@@ -285,11 +285,22 @@ extern "C" int tspgnn_set_params(tspgnn_handle h, const float* blob, int64_t n_f
   if (h->hp > 0) {
     const int hp = h->hp;
     std::vector<uint8_t> img;
+    std::vector<float> kc(2 * D * 4 * D);
     for (int c = 0; c < 2; ++c) {
+      // K.C with C = blockdiag(I - 11^T/64): every gate's 64 outputs leave the MMA with their row
+      // mean already removed, so the kernel's gate LayerNorms need one pass (sum of squares) only
+      for (int k = 0; k < 2 * D; ++k)
+        for (int g = 0; g < 4; ++g) {
+          const float* row = blob + o.cell_k[c] + static_cast<int64_t>(k) * 4 * D + g * D;
+          double m = 0.0;
+          for (int n = 0; n < D; ++n) m += row[n];
+          m /= D;
+          for (int n = 0; n < D; ++n) kc[static_cast<size_t>(k) * 4 * D + g * D + n] = static_cast<float>(row[n] - m);
+        }
       img.assign(static_cast<size_t>(hp) * 2 * 32768, 0);
       for (int p = 0; p < hp; ++p)
         for (int kb = 0; kb < 2; ++kb)
-          make_b_image(blob + o.cell_k[c], 4 * D, kb * 64, 0, 256, p, img.data() + (p * 2 + kb) * 32768);
+          make_b_image(kc.data(), 4 * D, kb * 64, 0, 256, p, img.data() + (p * 2 + kb) * 32768);
       if (dev_alloc(&h->d_wlstm[c], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
       CUDA_TRY(cudaMemcpy(h->d_wlstm[c], img.data(), img.size(), cudaMemcpyHostToDevice));
     }
