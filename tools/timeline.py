@@ -17,6 +17,16 @@ for which, name, roles in ((0, "K1 lnlstm", ["epiWG0", "epiWG1", "mma", "produce
     buf = np.zeros(148 * 4 * 64 * 8, dtype=np.int64)
     _lib.check(_lib.lib.tspgnn_debug_timeline(eng._h, which, buf.ctypes.data_as(ctypes.c_void_p), buf.size, eng._sptr()))
     tl = buf.reshape(148, 4, 64, 8)
+    gbase = tl[tl > 0].min()
+    spans = []
+    for cta in range(148):
+        t = tl[cta]
+        if (t > 0).any():
+            ntiles = int(((t[0] > 0).any(axis=1)).sum() + ((t[1] > 0).any(axis=1)).sum())
+            spans.append((int(t.max() - t[t > 0].min()), cta, ntiles))     # SM clocks have per-SM offsets
+    spans.sort(reverse=True)
+    print("==", name, "per-CTA (span cycles, cta, tiles): slowest 10 / fastest 4; mean span %.0f" % np.mean([x[0] for x in spans]))
+    print("   ", spans[:10], "...", spans[-4:])
     for cta in (0, 70, 147):
         t = tl[cta]
         base = t[t > 0].min() if (t > 0).any() else 0

@@ -565,16 +565,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
 // ====================================================================================
 // K2: message MLP chain (+ scatter / message store / vote)
 // ====================================================================================
+// 448 threads: three chain warpgroups (warps 0-3, 4-7, 8-11; tile n -> chain n % 3), warp 12 issues
+// the MMAs and owns the TMEM allocation (3 x 64 columns), warp 13 prefetches tile inputs.
+// A tile lives in ONE 32 KB shared-memory slot for its whole chain: the h planes arrive by bulk
+// copy, every hidden layer's activations overwrite them in place once that layer's MMA has
+// completed (the accumulator-full barrier is exactly that event), and the fp32 messages are staged
+// there for the scatter.  Five slots: three tiles in flight plus two prefetched.
+constexpr int K2_THREADS = 448;
+constexpr int K2_CHAINS = 3;
+
 template <int HP>
 struct K2Smem {
   static constexpr int W_BYTES = 4 * HP * 8192;            // [layer][plane] 8 KB images
   static constexpr int IN_BYTES = HP * PLANE_BYTES;        // h planes of one tile
-  static constexpr int NIN = 3;                            // input slots (tile n -> slot n % 3)
-  static constexpr int P_BYTES = 32768;                    // per-warpgroup pong buffer; also the fp32 message staging
-  static constexpr int IN_OFF = W_BYTES;
-  static constexpr int P_OFF = IN_OFF + NIN * IN_BYTES;
-  static constexpr int BAR_OFF = P_OFF + 2 * P_BYTES;
-  static constexpr int NBAR = 1 + 2 * NIN + 4;
+  static constexpr int SLOT_BYTES = 32768;                 // >= IN_BYTES, = fp32 staging of 128 x 64 messages
+  static constexpr int NSLOT = 5;
+  static constexpr int SLOT_OFF = W_BYTES;
+  static constexpr int BAR_OFF = SLOT_OFF + NSLOT * SLOT_BYTES;
+  static constexpr int NBAR = 1 + 2 * NSLOT + 2 * K2_CHAINS;
   static constexpr int BIAS_OFF = (BAR_OFF + 8 * NBAR + 16 + 15) & ~15;   // b[4][64] of this CTA's MLP
   static constexpr int TOTAL = BIAS_OFF + 4 * D * 4;
   static constexpr int DYN_BYTES = TOTAL + 128;
@@ -589,8 +597,8 @@ __device__ __forceinline__ uint32_t stage_off(int r, int chunk) {
 // ---- one warpgroup: epilogues of the layer chain of its tiles ------------------------------
 // ROLE 0 = V rows (V_msg_E, message stored), 1 = E rows (E_msg_V, scatter-add), 2 = E rows vote
 template <int HP, int ROLE>
-__device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint8_t* pbuf, uint64_t* acc_full,
-                                         uint64_t* act_ready, uint32_t tmem, int t0, int ntiles, int warp, int lane,
+__device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64_t* acc_full, uint64_t* act_ready,
+                                         uint64_t* slot_free, uint32_t tmem, int t0, int ntiles, int warp, int lane,
                                          uint32_t bias_s) {
   using L = K2Smem<HP>;
   constexpr int NL = (ROLE == 2) ? 3 : 4;
@@ -598,12 +606,13 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
   const int r = q4 * 32 + lane;
   const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 64;
   const int64_t n_rows = (ROLE == 0) ? a.nV : a.nE;
-  long long* tl = (q4 == 0 && lane == 0) ? a.timeline : nullptr;
-  const uint32_t p_s = ptx::smem_u32(pbuf), in_s = ptx::smem_u32(in_bufs);
+  long long* tl = (q4 == 0 && lane == 0 && e < 2) ? a.timeline : nullptr;
+  const uint32_t slots_s = ptx::smem_u32(slots);
   uint32_t step = 0;
-  for (int n = e; n < ntiles; n += 2) {
+  for (int n = e; n < ntiles; n += K2_CHAINS) {
     const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
-    const uint32_t i_s = in_s + (n % L::NIN) * L::IN_BYTES;
+    const int slot = n % L::NSLOT;
+    const uint32_t b_s = slots_s + slot * L::SLOT_BYTES;
     float v[64];
 #pragma unroll 1
     for (int l = 0; l < NL; ++l, ++step) {
@@ -614,7 +623,7 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
       const bool hidden = (ROLE == 2) || (l < 3);
       const bool feeds_mma = l < NL - 1;
       if (hidden) {
-        const uint32_t nxt = ((l & 1) ? i_s : p_s) + r * 16;   // layer l reads (l even ? in : pong), writes the other
+        const uint32_t nxt = b_s + r * 16;          // in place: this layer's MMA has finished reading the slot
         const uint32_t bl = bias_s + l * 256;       // broadcast LDS.128: four bias values per load
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
@@ -650,12 +659,13 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
       for (int j = 0; j < 64; ++j) s = fmaf(v[j], c_vote_tail.w4[j], s);
       if (grow < n_rows) a.vote[grow] = s;
     } else {
-      // stage the fp32 messages; each warp then walks its own 32 rows, two rows per instruction
-      // (a half-warp covers the 256 bytes of a row with 16-byte accesses)
+      // stage the fp32 messages in the tile's slot (the last MMA has finished reading it); each warp
+      // then walks its own 32 rows, two rows per instruction (a half-warp covers the 256 bytes of a
+      // row with 16-byte accesses)
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         const float4 bb = ptx::lds128f(bias_s + 3 * 256 + q * 16);
-        ptx::sts128f(p_s + stage_off(r, q),
+        ptx::sts128f(b_s + stage_off(r, q),
                      make_float4(v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w));
       }
       __syncwarp();
@@ -666,7 +676,7 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
         for (int i = 0; i < 16; ++i) {
           const int rr = 2 * i + hw;
           if (g0 + rr < n_rows) {
-            const float4 m = ptx::lds128f(p_s + stage_off(q4 * 32 + rr, c16));
+            const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
             *reinterpret_cast<float4*>(a.mV + (g0 + rr) * D + 4 * c16) = m;
           }
         }
@@ -686,7 +696,7 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
           const int s = __shfl_sync(0xffffffffu, my_s, rr);
           const int d = __shfl_sync(0xffffffffu, my_d, rr);
           if (s >= 0) {
-            const float4 m = ptx::lds128f(p_s + stage_off(q4 * 32 + rr, c16));
+            const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
             ptx::red_add_v4(a.xV + static_cast<int64_t>(d) * D + 4 * c16, m);
             if (s != cur_s) {
               if (cur_s >= 0) ptx::red_add_v4(a.xV + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
@@ -699,41 +709,40 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* in_bufs, uint
         }
         if (cur_s >= 0) ptx::red_add_v4(a.xV + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
       }
-      // the pong buffer is rewritten (in the operand layout) by this warpgroup's next tile
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
     }
+    // every warp of the chain is done with the slot: hand it back to the loader
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+    if (q4 == 0 && lane == 0) ptx::mbar_arrive(&slot_free[slot]);
     tl_mark(tl, e, n, 5);
   }
 }
 
 // Executed by the whole warp (converged); one elected lane issues the tcgen05 instructions.
 template <int HP>
-__device__ __forceinline__ void k2_mma(uint8_t* wsm, uint8_t* in_bufs, uint8_t* pbufs,
-                                       uint64_t* bar_w, uint64_t* in_full, uint64_t* in_free, uint64_t* acc_full,
-                                       uint64_t* act_ready, uint32_t tmem, int ntiles, int n_layers, long long* tl_) {
+__device__ __forceinline__ void k2_mma(uint8_t* wsm, uint8_t* slots, uint64_t* bar_w, uint64_t* slot_full,
+                                       uint64_t* acc_full, uint64_t* act_ready, uint32_t tmem, int ntiles, int n_layers,
+                                       long long* tl_) {
   using L = K2Smem<HP>;
   constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, 64);
   const bool leader = ptx::elect_one();
   long long* tl = leader ? tl_ : nullptr;
   ptx::mbar_wait(bar_w, 0);          // weight images (staged by the kernel prologue)
-  const uint64_t idesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(in_bufs), 2048, 128);
-  const uint64_t pdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(pbufs), 2048, 128);
+  const uint64_t sdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(slots), 2048, 128);
   const uint64_t bdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(wsm), 1024, 128);
-  const int npairs = (ntiles + 1) >> 1;
-  for (int pi = 0; pi < npairs; ++pi) {
+  const int nrounds = (ntiles + K2_CHAINS - 1) / K2_CHAINS;
+  for (int rd = 0; rd < nrounds; ++rd) {
     for (int l = 0; l < n_layers; ++l) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int n = 2 * pi + e;
+      for (int e = 0; e < K2_CHAINS; ++e) {
+        const int n = K2_CHAINS * rd + e;
         if (n >= ntiles) continue;
-        const int slot = n % L::NIN;
-        const uint32_t step = static_cast<uint32_t>(pi * n_layers + l);
-        if (l == 0) ptx::mbar_wait(&in_full[slot], (n / L::NIN) & 1);
+        const int slot = n % L::NSLOT;
+        const uint32_t step = static_cast<uint32_t>(rd * n_layers + l);
+        if (l == 0) ptx::mbar_wait(&slot_full[slot], (n / L::NSLOT) & 1);
         if (step > 0) ptx::mbar_wait(&act_ready[e], (step - 1) & 1);
         ptx::tcgen05_fence_after();
         if (ptx::elect_one()) {
-          const uint64_t adesc = (l & 1) ? pdesc0 + static_cast<uint32_t>((e * L::P_BYTES) >> 4)
-                                         : idesc0 + static_cast<uint32_t>((slot * L::IN_BYTES) >> 4);
+          const uint64_t adesc = sdesc0 + static_cast<uint32_t>((slot * L::SLOT_BYTES) >> 4);
           const uint64_t bdesc = bdesc0 + static_cast<uint32_t>((l * HP * 8192) >> 4);
           constexpr int NCOMB = (HP == 2) ? 3 : 1;
           const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
@@ -746,29 +755,27 @@ __device__ __forceinline__ void k2_mma(uint8_t* wsm, uint8_t* in_bufs, uint8_t* 
                                 bdesc + ((pb * 8192 + k * 2048) >> 4), IDESC, (cb | k) ? 1u : 0u);
           }
           ptx::umma_commit(&acc_full[e]);
-          if (l == 2) ptx::umma_commit(&in_free[slot]);   // last layer that reads the input slot
         }
         __syncwarp();
-        tl_mark(tl, 2, n, l);
+        if (e < 2) tl_mark(tl, 2, n, l);
       }
     }
   }
 }
 
 template <int HP>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
+__global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   using L = K2Smem<HP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* wsm = smem;
-  uint8_t* in_bufs = smem + L::IN_OFF;
-  uint8_t* pbufs = smem + L::P_OFF;
+  uint8_t* slots = smem + L::SLOT_OFF;
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* in_full = bar_w + 1;
-  uint64_t* in_free = in_full + L::NIN;
-  uint64_t* acc_full = in_free + L::NIN;
-  uint64_t* act_ready = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 2);
+  uint64_t* slot_full = bar_w + 1;
+  uint64_t* slot_free = slot_full + L::NSLOT;
+  uint64_t* acc_full = slot_free + L::NSLOT;
+  uint64_t* act_ready = acc_full + K2_CHAINS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + K2_CHAINS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
@@ -780,11 +787,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
 
   if (tid == 0) {
     ptx::mbar_init(bar_w, 1);
-    for (int s = 0; s < L::NIN; ++s) {
-      ptx::mbar_init(&in_full[s], 1);
-      ptx::mbar_init(&in_free[s], 1);
+    for (int s = 0; s < L::NSLOT; ++s) {
+      ptx::mbar_init(&slot_full[s], 1);
+      ptx::mbar_init(&slot_free[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < K2_CHAINS; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
       ptx::mbar_init(&act_ready[s], 4);
     }
@@ -795,11 +802,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
       for (int off = 0; off < L::W_BYTES; off += 16384) ptx::bulk_g2s(wsm + off, wimg + off, 16384, bar_w);
     }
   }
-  if (warp == 8) ptx::tmem_alloc(tmem_slot, 128);
+  if (warp == 12) ptx::tmem_alloc(tmem_slot, 256);
   {
     float* bias_sm = reinterpret_cast<float*>(smem + L::BIAS_OFF);
     const MlpBias& bias = c_mlp_bias[a.vote_mode ? 2 : (is_v ? 0 : 1)];
-    for (int i = tid; i < 4 * D; i += TC_THREADS) bias_sm[i] = bias.b[i >> 6][i & 63];
+    for (int i = tid; i < 4 * D; i += K2_THREADS) bias_sm[i] = bias.b[i >> 6][i & 63];
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -809,29 +816,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   ptx::grid_dependency_wait();       // prologue above overlaps the previous kernel's tail
   ptx::grid_launch_dependents();
 
-  if (warp < 8) {
-    uint8_t* pbuf = pbufs + (warp >> 2) * L::P_BYTES;
-    if (a.vote_mode) k2_chain<HP, 2>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane, bias_s);
-    else if (is_v) k2_chain<HP, 0>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane, bias_s);
-    else k2_chain<HP, 1>(a, in_bufs, pbuf, acc_full, act_ready, tmem, t0, ntiles, warp, lane, bias_s);
-  } else if (warp == 8) {
+  if (warp < 4 * K2_CHAINS) {
+    if (a.vote_mode) k2_chain<HP, 2>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
+    else if (is_v) k2_chain<HP, 0>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
+    else k2_chain<HP, 1>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
+  } else if (warp == 12) {
     if (ntiles > 0)
-      k2_mma<HP>(wsm, in_bufs, pbufs, bar_w, in_full, in_free, acc_full, act_ready, tmem, ntiles,
-                 a.vote_mode ? 3 : 4, a.timeline);
-  } else if (warp == 9) {
+      k2_mma<HP>(wsm, slots, bar_w, slot_full, acc_full, act_ready, tmem, ntiles, a.vote_mode ? 3 : 4, a.timeline);
+  } else if (warp == 13) {
     if (lane == 0) {
       for (int n = 0; n < ntiles; ++n) {
-        const int slot = n % L::NIN, use = n / L::NIN;
-        if (use >= 1) ptx::mbar_wait(&in_free[slot], (use - 1) & 1);
-        ptx::mbar_arrive_expect_tx(&in_full[slot], L::IN_BYTES);
-        ptx::bulk_g2s(in_bufs + slot * L::IN_BYTES, state + static_cast<int64_t>(t0 + n) * tile_bytes(HP), L::IN_BYTES,
-                      &in_full[slot]);
+        const int slot = n % L::NSLOT, use = n / L::NSLOT;
+        if (use >= 1) ptx::mbar_wait(&slot_free[slot], (use - 1) & 1);
+        ptx::mbar_arrive_expect_tx(&slot_full[slot], L::IN_BYTES);
+        ptx::bulk_g2s(slots + slot * L::SLOT_BYTES, state + static_cast<int64_t>(t0 + n) * tile_bytes(HP), L::IN_BYTES,
+                      &slot_full[slot]);
       }
     }
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) ptx::tmem_dealloc(tmem, 128);
+  if (warp == 12) ptx::tmem_dealloc(tmem, 256);
 }
 
 // ====================================================================================

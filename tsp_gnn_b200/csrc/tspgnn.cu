@@ -341,7 +341,10 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
   if (!edge_src || !edge_dst) return fail(TSPGNN_E_INVALID, "edge_src / edge_dst is NULL");
   // every edge row must connect two distinct vertices of its own instance: this is the
   // block-diagonal structure of EV (instance_loader.py:56-66), checked like graphnn.check_run
-  std::vector<int32_t> vptr(nV + 1, 0);
+  // CSR of EV^T (edge rows incident to every vertex): only the fp32 SIMT path segment-sums with it,
+  // the tensor-core path scatters from the edge side
+  const bool need_csr = (h->hp == 0);
+  std::vector<int32_t> vptr(need_csr ? nV + 1 : 1, 0);
   for (int k = 0; k < n_instances; ++k)
     for (int64_t e = eoff[k]; e < eoff[k + 1]; ++e) {
       const int64_t s = edge_src[e], t = edge_dst[e];
@@ -349,21 +352,28 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
         return fail(TSPGNN_E_INVALID,
                     "Matrix EV: edge row %lld connects columns (%lld,%lld) outside instance %d's vertex range [%lld,%lld)",
                     (long long)e, (long long)s, (long long)t, k, (long long)voff[k], (long long)voff[k + 1]);
-      vptr[s + 1]++;
-      vptr[t + 1]++;
+      if (need_csr) {
+        vptr[s + 1]++;
+        vptr[t + 1]++;
+      }
     }
-  for (int64_t v = 0; v < nV; ++v) vptr[v + 1] += vptr[v];
-  std::vector<int32_t> vidx(2 * nE), fill(vptr.begin(), vptr.end() - 1);
-  for (int64_t e = 0; e < nE; ++e) {
-    vidx[fill[edge_src[e]]++] = static_cast<int32_t>(e);
-    vidx[fill[edge_dst[e]]++] = static_cast<int32_t>(e);
+  std::vector<int32_t> vidx;
+  if (need_csr) {
+    for (int64_t v = 0; v < nV; ++v) vptr[v + 1] += vptr[v];
+    vidx.resize(2 * nE);
+    std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
+    for (int64_t e = 0; e < nE; ++e) {
+      vidx[fill[edge_src[e]]++] = static_cast<int32_t>(e);
+      vidx[fill[edge_dst[e]]++] = static_cast<int32_t>(e);
+    }
   }
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaDeviceSynchronize());
-  drop_graphs(h);
   const int64_t nE_pad = (nE + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
   const int64_t nV_pad = (nV + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+  bool realloc_happened = false;
   if (nE_pad > h->cap_E) {
+    realloc_happened = true;
     if (dev_alloc(&h->d_src, nE_pad) || dev_alloc(&h->d_dst, nE_pad) || dev_alloc(&h->d_vidx, 2 * nE_pad) ||
         dev_alloc(&h->Eh, nE_pad * D) || dev_alloc(&h->vote, nE_pad) || dev_alloc(&h->d_W, nE_pad) ||
         dev_alloc(&h->d_C, nE_pad))
@@ -376,6 +386,7 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
     h->cap_E = nE_pad;
   }
   if (nV_pad > h->cap_V) {
+    realloc_happened = true;
     if (dev_alloc(&h->d_vptr, nV_pad + 1) || dev_alloc(&h->Vh, nV_pad * D) || dev_alloc(&h->mV, nV_pad * D) ||
         dev_alloc(&h->xV, nV_pad * D))
       return TSPGNN_E_CUDA;
@@ -392,12 +403,17 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
       return TSPGNN_E_CUDA;
     h->cap_B = n_instances;
   }
+  // the captured timestep graphs bake in pointers and sizes: they survive a re-plan with the same
+  // geometry (the usual case: fixed batch shape, new instances) and are dropped otherwise
+  if (realloc_happened || nE != h->nE || nV != h->nV || n_instances != h->B) drop_graphs(h);
   CUDA_TRY(cudaMemset(h->d_src, 0, nE_pad * 4));
   CUDA_TRY(cudaMemset(h->d_dst, 0, nE_pad * 4));
   CUDA_TRY(cudaMemcpy(h->d_src, edge_src, nE * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(h->d_dst, edge_dst, nE * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->d_vptr, vptr.data(), (nV + 1) * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(h->d_vidx, vidx.data(), 2 * nE * 4, cudaMemcpyHostToDevice));
+  if (need_csr) {
+    CUDA_TRY(cudaMemcpy(h->d_vptr, vptr.data(), (nV + 1) * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->d_vidx, vidx.data(), 2 * nE * 4, cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaMemcpy(h->d_eoff, eoff.data(), (n_instances + 1) * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(h->xV, 0, nV_pad * D * 4));
   CUDA_TRY(cudaMemset(h->mV, 0, nV_pad * D * 4));
@@ -434,10 +450,11 @@ static int check_ready(tspgnn_ctx* h) {
 // Launch with programmatic stream serialization: the kernel may start (and run its prologue up to
 // griddepcontrol.wait) while the preceding kernel of the stream is still draining.
 template <typename Args>
-static cudaError_t launch_pdl(void (*kernel)(const Args), int grid, int smem, cudaStream_t s, const Args& a) {
+static cudaError_t launch_pdl(void (*kernel)(const Args), int grid, int threads, int smem, cudaStream_t s,
+                              const Args& a) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -487,7 +504,7 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, long long* tim
   a.vote_mode = vote ? 1 : 0;
   int grid;
   role_split(h, a.tilesE, a.tilesV, 0.8, grid, a.e_ctas);
-  CUDA_TRY(launch_pdl(tc_mlp_kernel<HP>, grid, K2Smem<HP>::DYN_BYTES, s, a));
+  CUDA_TRY(launch_pdl(tc_mlp_kernel<HP>, grid, K2_THREADS, K2Smem<HP>::DYN_BYTES, s, a));
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -510,7 +527,7 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, long long* timeline = nul
   a.tilesV = h->tilesV;
   int grid;
   role_split(h, a.tilesE, a.tilesV, 1.35, grid, a.e_ctas);
-  CUDA_TRY(launch_pdl(tc_lnlstm_kernel<HP>, grid, K1Smem<HP>::DYN_BYTES, s, a));
+  CUDA_TRY(launch_pdl(tc_lnlstm_kernel<HP>, grid, TC_THREADS, K1Smem<HP>::DYN_BYTES, s, a));
   LAUNCH_CHECK(h);
   return 0;
 }
