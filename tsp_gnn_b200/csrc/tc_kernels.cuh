@@ -65,6 +65,7 @@ struct K1Args {
   const int32_t* dst;
   int64_t nE, nV;
   int tilesE, tilesV, e_ctas;
+  int clampE, clampV;    // 1: clamp the logistic exponents of the i / f gates (large LayerNorm gamma / beta)
   long long* timeline;   // optional clock64() trace (tools/timeline.py), nullptr in production
 };
 
@@ -188,9 +189,25 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
   load_idx(t0, si, di);
   for (int n = 0; n < ntiles; ++n) {
     const int tile = t0 + n;
-    // ---- x operand (k-block 0) ---------------------------------------------------------
+    // ---- h operand (k-block 1): the h planes of the tile image, one bulk copy ------------
     {
       const int seq = 2 * n, slot = seq % L::NSLOT, use = seq / L::NSLOT;
+      if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
+      tl_mark(tl, 3, n, 3);
+      if (lane == 0) {
+        if (gw == 0) {
+          ptx::mbar_arrive_expect_tx(&full[slot], L::SLOT_BYTES);
+          ptx::bulk_g2s(ring + slot * L::SLOT_BYTES, state + static_cast<int64_t>(tile) * tile_bytes(HP),
+                        L::SLOT_BYTES, &full[slot]);
+        } else {
+          ptx::mbar_arrive(&full[slot]);
+        }
+      }
+      __syncwarp();
+    }
+    // ---- x operand (k-block 0) ---------------------------------------------------------
+    {
+      const int seq = 2 * n + 1, slot = seq % L::NSLOT, use = seq / L::NSLOT;
       int sn[6], dn[6];
 #pragma unroll
       for (int gi = 0; gi < 6; ++gi) sn[gi] = dn[gi] = 0;
@@ -209,22 +226,6 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
         si[gi] = sn[gi];
         di[gi] = dn[gi];
       }
-    }
-    // ---- h operand (k-block 1): the h planes of the tile image, one bulk copy ------------
-    {
-      const int seq = 2 * n + 1, slot = seq % L::NSLOT, use = seq / L::NSLOT;
-      if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
-      tl_mark(tl, 3, n, 3);
-      if (lane == 0) {
-        if (gw == 0) {
-          ptx::mbar_arrive_expect_tx(&full[slot], L::SLOT_BYTES);
-          ptx::bulk_g2s(ring + slot * L::SLOT_BYTES, state + static_cast<int64_t>(tile) * tile_bytes(HP),
-                        L::SLOT_BYTES, &full[slot]);
-        } else {
-          ptx::mbar_arrive(&full[slot]);
-        }
-      }
-      __syncwarp();
     }
   }
 }
@@ -251,10 +252,12 @@ __device__ __forceinline__ void k1_mma(uint8_t* wsm, uint8_t* ring, uint64_t* ba
     tl_mark(tl, 2, n, 1);
     const uint32_t d_tmem = tmem + acc * 256;
 #pragma unroll
-    for (int kb = 0; kb < 2; ++kb) {
-      const int seq = 2 * n + kb, slot = seq % L::NSLOT, use = seq / L::NSLOT;
+    for (int half = 0; half < 2; ++half) {
+      // the h k-block first: its bulk copy lands long before the gathered x operand is built
+      const int kb = 1 - half;
+      const int seq = 2 * n + half, slot = seq % L::NSLOT, use = seq / L::NSLOT;
       ptx::mbar_wait(&full[slot], use & 1);
-      tl_mark(tl, 2, n, 2 + 2 * kb);
+      tl_mark(tl, 2, n, 2 + 2 * half);
       ptx::tcgen05_fence_after();
       if (ptx::elect_one()) {
         // (A plane, B plane): small cross terms first, then hi*hi
@@ -268,13 +271,13 @@ __device__ __forceinline__ void k1_mma(uint8_t* wsm, uint8_t* ring, uint64_t* ba
           for (int k = 0; k < 4; ++k)
             ptx::umma_bf16_ss(d_tmem, aslot + ((pa * PLANE_BYTES + k * 4096) >> 4),
                               bdesc0 + (((pb * 2 + kb) * 32768 + k * 8192) >> 4), IDESC,
-                              (kb | cb | k) ? 1u : 0u);
+                              (half | cb | k) ? 1u : 0u);
         }
         ptx::umma_commit(&empty[slot]);
-        if (kb == 1) ptx::umma_commit(&acc_full[acc]);
+        if (half == 1) ptx::umma_commit(&acc_full[acc]);
       }
       __syncwarp();
-      tl_mark(tl, 2, n, 3 + 2 * kb);
+      tl_mark(tl, 2, n, 3 + 2 * half);
     }
   }
 }
@@ -331,14 +334,16 @@ __device__ __forceinline__ float row_rstd_centered64(uint32_t taddr) {
   return rsqrtf((qt.x + qt.y) * (1.0f / 64) + LN_EPS);
 }
 
-// 1 + 2^t for two values (t = -x log2 e, so this is 1 + exp(-x)); the exponent is clamped so that
-// a product of two results stays finite
+// 1 + 2^t for two values (t = -x log2 e, so this is 1 + exp(-x)).  CLAMP bounds the exponent so that
+// the product of two results stays finite; tspgnn_set_params turns it off when the LayerNorm
+// parameters bound |t| well below that (|LN(z)| <= sqrt(63) for 64 features).
+template <bool CLAMP>
 __device__ __forceinline__ float2 one_plus_ex2(float2 t) {
-  return __fadd2_rn(make_float2(ptx::ex2_approx(fminf(t.x, 60.f)), ptx::ex2_approx(fminf(t.y, 60.f))),
-                    make_float2(1.0f, 1.0f));
+  if (CLAMP) t = make_float2(fminf(t.x, 60.f), fminf(t.y, 60.f));
+  return __fadd2_rn(make_float2(ptx::ex2_approx(t.x), ptx::ex2_approx(t.y)), make_float2(1.0f, 1.0f));
 }
 
-template <int HP, int CELL>
+template <int HP, int CELL, bool CLAMP>
 __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
                                             uint64_t* acc_empty, int warp, int lane, long long* tl_, uint32_t ln_s) {
   // ln_s: shared-memory copy of this cell's LayerNorm parameters, gamma[g][j] at ln_s + (g*64+j)*4,
@@ -413,7 +418,7 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
         const float2 cold = (p & 1) ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
         // c*sigmoid(f) + sigmoid(i)*relu(j) = (c*Q + relu(j)*P) / (P*Q), P = 1+e^-f, Q = 1+e^-i:
         // one reciprocal for the two logistic functions
-        const float2 P = one_plus_ex2(fn), Q = one_plus_ex2(in);   // in / fn are already -x log2 e
+        const float2 P = one_plus_ex2<CLAMP>(fn), Q = one_plus_ex2<CLAMP>(in);   // in / fn are already -x log2 e
         const float2 den = __fmul2_rn(P, Q);
         const float2 num = __ffma2_rn(cold, Q, __fmul2_rn(ptx::relu2(jn), P));
         const float2 cn2 = __fmul2_rn(num, make_float2(ptx::rcp_approx(den.x), ptx::rcp_approx(den.y)));
@@ -461,7 +466,7 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
         const float2 on = __ffma2_rn(__fmul2_rn(make_float2(vo[2 * p], vo[2 * p + 1]), make_float2(rs3, rs3)), go, bo);
         c2[p] = __ffma2_rn(__ffma2_rn(make_float2(cs[2 * p], cs[2 * p + 1]), make_float2(crs, crs),
                                       make_float2(cm, cm)), gs, bs);
-        const float2 eo = one_plus_ex2(on);                         // on is already -x log2 e
+        const float2 eo = one_plus_ex2<false>(on);   // on is already -x log2 e; 2^t = inf gives h = 0, the right limit
         const float2 hn = __fmul2_rn(ptx::relu2(c2[p]), make_float2(ptx::rcp_approx(eo.x), ptx::rcp_approx(eo.y)));
         ptx::split_bf16x2_p(hn, hi[p], lo[p]);
       }
@@ -545,8 +550,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
 
   if (warp < 8) {
     ptx::setmaxnreg_inc<200>();   // ... 256 x (200 - 168) = 8192 taken by the two epilogue warpgroups
-    if (is_v) k1_epilogue<HP, 0>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
-    else k1_epilogue<HP, 1>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+    const bool clamp = (is_v ? a.clampV : a.clampE) != 0;
+    if (is_v) {
+      if (clamp) k1_epilogue<HP, 0, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+      else k1_epilogue<HP, 0, false>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+    } else {
+      if (clamp) k1_epilogue<HP, 1, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+      else k1_epilogue<HP, 1, false>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+    }
   } else {
     ptx::setmaxnreg_dec<104>();   // 128 x (168 - 104) = 8192 registers back to the CTA pool ...
     if (warp == 8) {

@@ -145,6 +145,7 @@ struct tspgnn_ctx {
   float *d_W = nullptr, *d_C = nullptr, *d_logits = nullptr, *d_preds = nullptr;
   int64_t cap_E = 0, cap_V = 0, cap_B = 0;
   int64_t launches = 0;
+  int clamp_cell[2] = {1, 1};   // per cell: logistic exponents of the i / f gates need clamping
   std::map<int, cudaGraphExec_t> step_graphs;
   int64_t plan_generation = 0;
 };
@@ -264,6 +265,19 @@ extern "C" int tspgnn_set_params(tspgnn_handle h, const float* blob, int64_t n_f
       memcpy(h->h_ln[c].gamma[g], blob + o.cell_gamma[c][g], D * 4);
       memcpy(h->h_ln[c].beta[g], blob + o.cell_beta[c][g], D * 4);
     }
+  for (int c = 0; c < 2; ++c) {
+    // |LN(z)_j| <= sqrt(63) for 64 features, so the exponent of 2^(-x log2 e) of gate g is bounded by
+    // log2(e) * (sqrt(63) |gamma_j| + |beta_j| (+ forget bias)); the kernel multiplies (1 + 2^t_f)(1 + 2^t_i)
+    double bound[2] = {0.0, 0.0};
+    const int gates[2] = {0, 2};
+    for (int q = 0; q < 2; ++q)
+      for (int j = 0; j < D; ++j) {
+        const double t = 1.4426950408889634 * (7.9372539 * std::fabs(blob[o.cell_gamma[c][gates[q]] + j]) +
+                                               std::fabs(blob[o.cell_beta[c][gates[q]] + j]) + (q == 1 ? 1.0 : 0.0));
+        bound[q] = std::max(bound[q], t);
+      }
+    h->clamp_cell[c] = (bound[0] + bound[1] < 100.0) ? 0 : 1;
+  }
   for (int m = 0; m < 2; ++m)
     for (int l = 0; l < 4; ++l) memcpy(h->h_bias[m].b[l], blob + o.msg_b[m][l], D * 4);
   for (int l = 0; l < 3; ++l) memcpy(h->h_bias[2].b[l], blob + o.vote_b[l], D * 4);
@@ -525,6 +539,8 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, long long* timeline = nul
   a.nV = h->nV;
   a.tilesE = h->tilesE;
   a.tilesV = h->tilesV;
+  a.clampV = h->clamp_cell[0];
+  a.clampE = h->clamp_cell[1];
   int grid;
   role_split(h, a.tilesE, a.tilesV, 1.35, grid, a.e_ctas);
   CUDA_TRY(launch_pdl(tc_lnlstm_kernel<HP>, grid, TC_THREADS, K1Smem<HP>::DYN_BYTES, s, a));
