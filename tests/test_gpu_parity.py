@@ -218,3 +218,30 @@ def test_cuda_path_matches_reference_graph_code_fixtures(mode):
         assert np.abs(got["predictions"] - gold[name + "/predictions"]).max() <= TOL_PRED[mode]
         assert state_err(got["V_h"], gold[name + "/V_h"]) <= TOL_STATE[mode]
         assert state_err(got["E_c"][:48], gold[name + "/E_c_head"]) <= TOL_STATE[mode]
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_large_layernorm_gains_take_the_clamped_path(mode):
+    """gamma of the input / forget gates scaled x12: tspgnn_set_params must select the kernel variant that
+    clamps the logistic exponents (the unclamped (1+2^a)(1+2^b) product would overflow); gates saturate."""
+    EV, W, C, y, nv, ne = inst.synth_batch([11, 12, 13], seed=3)
+    params = orc.init_params(64, seed=4, perturb_ln=True)
+    for v in ("V", "E"):
+        for g in ("input", "forget", "output"):
+            params["TSP/%s_cell/layer_norm_basic_lstm_cell/%s/gamma" % (v, g)] *= 12.0
+    got = run_engine(mode, params, EV, W, C, nv, ne, 5)
+    ref = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, 5, dtype=np.float64)
+    assert np.all(np.isfinite(got["E_h"])) and np.all(np.isfinite(got["V_c"]))
+    tol_p, tol_s = (2e-4, 2e-3) if mode == "bf16x3" else (2e-2, 3e-1)   # saturated gates amplify rounding
+    assert np.abs(got["predictions"] - ref["predictions"]).max() <= tol_p
+    assert state_err(got["E_h"], ref["E_h"]) <= tol_s
+
+
+def test_generalisation_size_n80_matches_oracle():
+    """BASELINE config 5 family (larger graphs than trained on): 6 instances of n=80, 3160 edges each."""
+    EV, W, C, y, nv, ne = inst.synth_batch([80] * 6, seed=9)
+    params = orc.init_params(64, seed=2)
+    got = run_engine("bf16x3", params, EV, W, C, nv, ne, 32)
+    ref = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, 32, dtype=np.float64)
+    assert np.abs(got["predictions"] - ref["predictions"]).max() <= 1e-4
+    assert state_err(got["V_h"], ref["V_h"]) <= 1e-4
