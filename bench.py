@@ -238,8 +238,14 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         ach = k1_b / (k1_ms * 1e-3) / 1e9
+        traffic = None        # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "tc_lnlstm_kernel<%d>" % (2 if args.mode == "bf16x3" else 1))
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "tc_lnlstm_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "frac": ach / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": k1_b, "kernel_ms": k1_ms, "mlp_kernel_ms": k2_ms,
                 "step_frac_of_hbm_floor": (total_b / (peak * 1e9)) / (dev_ms * 1e-3 / (T_STEPS * args.steps))}
 
