@@ -116,7 +116,7 @@ struct K1Smem {
   static constexpr int NSLOT = (HP == 2) ? 3 : 6;          // ring of operand slots: x(t), h(t), x(t+1), ...
   static constexpr int RING_OFF = W_BYTES;
   static constexpr int BAR_OFF = RING_OFF + NSLOT * SLOT_BYTES;
-  static constexpr int NBAR = 1 + 2 * NSLOT + 4;
+  static constexpr int NBAR = 1 + 2 * NSLOT + 4 + 1;
   static constexpr int LN_OFF = (BAR_OFF + 8 * NBAR + 16 + 15) & ~15;   // gamma[5][64], beta[5][64] of this CTA's cell
   static constexpr int TOTAL = LN_OFF + 2 * 5 * D * 4;
   static constexpr int DYN_BYTES = TOTAL + 128;            // slack for 128-B alignment
@@ -165,9 +165,55 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
   }
 }
 
+// The x operand of a CTA's FIRST tile is built by the eight epilogue warps, which have nothing to do
+// until the first accumulator is ready and have the registers to keep every load in flight: the
+// first gather drops from three L2 round trips to one and the gather warps start on tile 1 at once.
+template <int HP, bool IS_V>
+__device__ __forceinline__ void k1_boot_fill(const K1Args& a, uint8_t* slot, int warp, int lane, int tile) {
+  const int r8 = lane & 7, cq = lane >> 3;
+  const uint32_t slot_s = ptx::smem_u32(slot);
+  const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
+  int s_[2] = {0, 0}, d_[2] = {0, 0};
+  if (!IS_V) {
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      s_[gi] = __ldg(a.src + row0 + (2 * warp + gi) * 8 + r8);
+      d_[gi] = __ldg(a.dst + row0 + (2 * warp + gi) * 8 + r8);
+    }
+  }
+#pragma unroll
+  for (int gi = 0; gi < 2; ++gi) {
+    const int row = (2 * warp + gi) * 8 + r8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int chunk = cq + 4 * j;
+      float x[8];
+      if (IS_V) {
+        float4* p = reinterpret_cast<float4*>(a.xV + (row0 + row) * D + chunk * 8);
+        const float4 u0 = p[0], u1 = p[1];
+        p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
+        x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
+      } else {
+        const float4* ps = reinterpret_cast<const float4*>(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8);
+        const float4* pd = reinterpret_cast<const float4*>(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8);
+        const float4 u0 = __ldg(ps), u1 = __ldg(ps + 1), w0 = __ldg(pd), w1 = __ldg(pd + 1);
+        x[0] = u0.x + w0.x; x[1] = u0.y + w0.y; x[2] = u0.z + w0.z; x[3] = u0.w + w0.w;
+        x[4] = u1.x + w1.x; x[5] = u1.y + w1.y; x[6] = u1.z + w1.z; x[7] = u1.w + w1.w;
+      }
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      const uint32_t off = slot_s + chunk * 2048 + row * 16;
+      ptx::sts128(off, hi);
+      if (HP == 2) ptx::sts128(off + PLANE_BYTES, lo);
+    }
+  }
+}
+
 template <int HP, bool IS_V>
 __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uint8_t* ring, uint64_t* full,
-                                            uint64_t* empty, int t0, int ntiles, int gw, int lane) {
+                                            uint64_t* empty, uint64_t* boot, int t0, int ntiles, int gw, int lane) {
   using L = K1Smem<HP>;
   long long* tl = (gw == 0 && lane == 0) ? a.timeline : nullptr;
   const int r8 = lane & 7;
@@ -186,8 +232,7 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
       }
     }
   };
-  load_idx(t0, si, di);
-  for (int n = 0; n < ntiles; ++n) {
+  for (int n = 0; n < ntiles; ++n) {   // (tile 0 needs no indices here: the epilogue warps build its operand)
     const int tile = t0 + n;
     // ---- h operand (k-block 1): the h planes of the tile image, one bulk copy ------------
     {
@@ -215,9 +260,13 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
       tl_mark(tl, 3, n, 0);
       if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
       tl_mark(tl, 3, n, 1);
-      k1_fill_x<HP, IS_V>(ring + slot * L::SLOT_BYTES, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, a.mV, a.xV,
-                          si, di);
-      ptx::fence_proxy_async_smem();
+      if (n == 0) {
+        if (gw == 0) ptx::mbar_wait(boot, 0);     // tile 0: operand written by the epilogue warps (k1_boot_fill)
+      } else {
+        k1_fill_x<HP, IS_V>(ring + slot * L::SLOT_BYTES, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, a.mV, a.xV,
+                            si, di);
+        ptx::fence_proxy_async_smem();
+      }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full[slot]);
       tl_mark(tl, 3, n, 2);
@@ -495,7 +544,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
   uint64_t* empty = full + L::NSLOT;
   uint64_t* acc_full = empty + L::NSLOT;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* boot = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(boot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
@@ -507,6 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
 
   if (tid == 0) {
     ptx::mbar_init(bar_w, 1);
+    ptx::mbar_init(boot, 8);
     for (int s = 0; s < L::NSLOT; ++s) {
       ptx::mbar_init(&full[s], NUM_GATHER_WARPS);
       ptx::mbar_init(&empty[s], 1);
@@ -550,6 +601,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
 
   if (warp < 8) {
     ptx::setmaxnreg_inc<200>();   // ... 256 x (200 - 168) = 8192 taken by the two epilogue warpgroups
+    if (ntiles > 0) {
+      uint8_t* x0 = ring + (1 % L::NSLOT) * L::SLOT_BYTES;       // ring slot of sequence number 1 = x operand of tile 0
+      if (is_v) k1_boot_fill<HP, true>(a, x0, warp, lane, t0);
+      else k1_boot_fill<HP, false>(a, x0, warp, lane, t0);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(boot);
+    }
     const bool clamp = (is_v ? a.clampV : a.clampE) != 0;
     if (is_v) {
       if (clamp) k1_epilogue<HP, 0, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
@@ -564,8 +623,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
       if (ntiles > 0)
         k1_mma<HP>(wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles, a.timeline);
     } else {
-      if (is_v) k1_producer<HP, true>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
-      else k1_producer<HP, false>(a, state, ring, full, empty, t0, ntiles, warp - 9, lane);
+      if (is_v) k1_producer<HP, true>(a, state, ring, full, empty, boot, t0, ntiles, warp - 9, lane);
+      else k1_producer<HP, false>(a, state, ring, full, empty, boot, t0, ntiles, warp - 9, lane);
     }
   }
   ptx::tcgen05_fence_before();
