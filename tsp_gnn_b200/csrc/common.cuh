@@ -36,9 +36,4 @@ struct EInit {      // model.py:33-43, sizes 2->8->16->32->64
   float w4[32][64], b4[64];
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) {
-  // 1/(1+exp(-x)); __expf/__frcp_rn keep ~1e-7 relative error, inf-safe for x -> -inf.
-  return __frcp_rn(1.0f + __expf(-x));
-}
-
 }  // namespace tspgnn

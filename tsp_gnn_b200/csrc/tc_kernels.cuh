@@ -47,13 +47,6 @@ __host__ __device__ inline uint32_t wimg_off(int n, int k, int n_rows) {
   return static_cast<uint32_t>((k >> 3) * (n_rows * 16) + n * 16 + (k & 7) * 2);
 }
 
-__device__ __forceinline__ float fast_rcp(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.0f + __expf(-x)); }
-
 struct K1Args {
   uint8_t* stateE;
   uint8_t* stateV;

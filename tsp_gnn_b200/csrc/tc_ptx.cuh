@@ -65,17 +65,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// shared -> global, tracked by the per-thread bulk async-group
-__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
-               "r"(smem_u32(smem_src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// the shared-memory source of all committed bulk stores has been read
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // ------------------------------- TMEM ---------------------------------------------
 // one full warp; writes the allocated TMEM base address to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -89,20 +78,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 
 // ------------------------------- UMMA ---------------------------------------------
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout) for a K-major
-// operand stored as rows of 64 bf16 (128 B) with the 128-byte swizzle: 8-row groups are
-// 1024 B apart (SBO); LBO is unused for swizzled K-major layouts.
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address      [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                       // LBO (ignored)      [16,30)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO = 1024 B       [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version [46,48)
-  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B       [61,64)
-  return d;
-}
-
-// Same descriptor for the un-swizzled ("interleaved") K-major canonical layout, in 16-byte
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout) for the un-swizzled
+// ("interleaved") K-major canonical layout, in 16-byte
 // units ((8,n),2):((1,SBO),LBO): a core matrix is 8 rows x 16 B stored contiguously (128 B),
 // 8-row groups are SBO bytes apart and the two 16-byte K chunks of one MMA are LBO bytes apart.
 __device__ __forceinline__ uint64_t umma_desc_k_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -154,38 +131,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ------------------------------- TMEM loads ---------------------------------------
-// 32x32b: thread t of warp w reads lane 32*(w%4)+t, N consecutive 32-bit columns.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
+// 32x32b shape: thread t of warp w reads lane 32*(w%4)+t, N consecutive 32-bit columns.
 // 64 columns as two x32 loads in flight, one wait
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
   uint32_t r[64];
@@ -277,74 +223,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       : "memory");
 }
 
-// ------------------------------- 16-lane TMEM accesses ---------------------------------
-// .16x256b.xN: one warp touches 16 lanes x 8N columns.  Thread t (t0 = t & 3, t1 = t >> 2) gets
-//   reg[4k + 2hi + j] = (lane base + t1 + 8*hi, column c0 + 8k + 2*t0 + j),  k < N, hi < 2, j < 2
-// (verified on B200 by tools/microbench/tmem_layout.cu, including a lane base of +16 inside the
-// warp's 32-lane sub-partition).  A row is spread over the 4 threads of a quad, so two warps can
-// share one 32-lane quarter and row reductions are two shuffles.
-__device__ __forceinline__ void tmem_ld_q8(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// three 16-column pieces (x2) in flight, one wait
-__device__ __forceinline__ void tmem_ld_q2x3(uint32_t a0, uint32_t a1, uint32_t a2, float (&v0)[8], float (&v1)[8],
-                                             float (&v2)[8]) {
-  uint32_t r[24];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
-      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
-      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
-      : "r"(a0), "r"(a1), "r"(a2)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v0[i] = __uint_as_float(r[i]);
-    v1[i] = __uint_as_float(r[8 + i]);
-    v2[i] = __uint_as_float(r[16 + i]);
-  }
-}
-__device__ __forceinline__ void tmem_ld_q2x2(uint32_t a0, uint32_t a1, float (&v0)[8], float (&v1)[8]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
-      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(a0), "r"(a1)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    v0[i] = __uint_as_float(r[i]);
-    v1[i] = __uint_as_float(r[8 + i]);
-  }
-}
-__device__ __forceinline__ void tmem_st_q2(uint32_t taddr, const float (&v)[8]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n\t"
-      "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-      : "memory");
-}
-
 // ------------------------------- register re-allocation ------------------------------
 // executed by every warp of a warpgroup (4 consecutive warps, first one a multiple of 4)
 template <int N>
@@ -367,11 +245,6 @@ __device__ __forceinline__ void sts128f(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
-__device__ __forceinline__ float2 lds64f(uint32_t saddr) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
-  return v;
-}
 __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -390,11 +263,6 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------- misc ----------------------------------------------
-// xV[v] += {a, b}: vector reduction to global memory (sm_90+)
-__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-
 // fp32 pair -> bf16x2 hi (round to nearest) and bf16x2 lo = rn(x - hi); element a in the
 // low half-word (lower address), b in the high half-word.
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -414,12 +282,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// logistic function of two values: 1 / (1 + 2^(-x log2 e)); packed fp32x2 for the FMA-pipe part
-__device__ __forceinline__ float2 sigmoid2(float2 x) {
-  const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-  const float2 e = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
-  return make_float2(rcp_approx(e.x), rcp_approx(e.y));
 }
 __device__ __forceinline__ float2 relu2(float2 x) { return make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)); }
 
