@@ -142,11 +142,11 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
           x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
           x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
         } else {
-          const float4* ps = reinterpret_cast<const float4*>(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8);
-          const float4* pd = reinterpret_cast<const float4*>(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8);
-          const float4 u0 = __ldg(ps), u1 = __ldg(ps + 1), w0 = __ldg(pd), w1 = __ldg(pd + 1);
-          x[0] = u0.x + w0.x; x[1] = u0.y + w0.y; x[2] = u0.z + w0.z; x[3] = u0.w + w0.w;
-          x[4] = u1.x + w1.x; x[5] = u1.y + w1.y; x[6] = u1.z + w1.z; x[7] = u1.w + w1.w;
+          float u[8], w[8];
+          ptx::ldg256(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u);
+          ptx::ldg256(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = u[i] + w[i];
         }
         uint4 hi, lo;
         split8(x, hi, lo);
@@ -189,11 +189,11 @@ __device__ __forceinline__ void k1_boot_fill(const K1Args& a, uint8_t* slot, int
         x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
         x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
       } else {
-        const float4* ps = reinterpret_cast<const float4*>(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8);
-        const float4* pd = reinterpret_cast<const float4*>(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8);
-        const float4 u0 = __ldg(ps), u1 = __ldg(ps + 1), w0 = __ldg(pd), w1 = __ldg(pd + 1);
-        x[0] = u0.x + w0.x; x[1] = u0.y + w0.y; x[2] = u0.z + w0.z; x[3] = u0.w + w0.w;
-        x[4] = u1.x + w1.x; x[5] = u1.y + w1.y; x[6] = u1.z + w1.z; x[7] = u1.w + w1.w;
+        float u[8], w[8];
+        ptx::ldg256(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8, u);
+        ptx::ldg256(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = u[i] + w[i];
       }
       uint4 hi, lo;
       split8(x, hi, lo);

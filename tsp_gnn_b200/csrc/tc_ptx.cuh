@@ -256,6 +256,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
+// 32-byte read-only global load (LDG.E.256, sm_100): one request per 32-byte sector instead of two
+// 16-byte loads that each fetch it
+__device__ __forceinline__ void ldg256(const float* p, float (&f)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p));
+}
+
 // ------------------------------- programmatic dependent launch -------------------------
 // wait: blocks until the grids this one depends on have completed and flushed their memory;
 // everything before it (barrier init, TMEM allocation, weight staging) overlaps their tail.
