@@ -247,6 +247,8 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": "tc_lnlstm_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": k1_b, "kernel_ms": k1_ms, "mlp_kernel_ms": k2_ms,
+                "timing": "CUDA events around single launches on the engine's stream, 20 launches each, right after "
+                          "the timed region (tspgnn_time_kernel); inside the graph the two kernels cannot be bracketed",
                 "step_frac_of_hbm_floor": (total_b / (peak * 1e9)) / (dev_ms * 1e-3 / (T_STEPS * args.steps))}
 
     # ---------------- end-to-end leg through the host-buffer C-ABI call -----------------
