@@ -92,6 +92,44 @@ int tspgnn_get_states(tspgnn_handle h, float* dVh, float* dVc, float* dEh, float
 int tspgnn_set_states(tspgnn_handle h, const float* dVh, const float* dVc, const float* dEh,
                       const float* dEc, void* stream);
 
+/* ---- training step: replaces sess.run([train_step, loss, ...]) (train.py:35-42, model.py:157-167) ----
+ *
+ * tspgnn_train_forward : the forward pass of tspgnn_forward_device that also keeps, per timestep,
+ *                        the recurrent state the reverse pass needs (tf.while_loop's loop stacks).
+ * tspgnn_backward      : loss = sum_k xent(logit_k, route_exists_k) / global_batch (model.py:157) and
+ *                        d loss / d every trainable variable (tf.gradients, model.py:166) into a flat
+ *                        device blob laid out like the parameter blob.  global_batch is the divisor
+ *                        of reduce_mean: the number of instances of the WHOLE batch when instances are
+ *                        sharded over ranks (then the sum of the ranks' blobs is the batch gradient);
+ *                        <= 0 means this handle's own batch.  d_grads NULL = the handle's own buffer
+ *                        (tspgnn_grad_buffer).  d_loss (device, 1 float) may be NULL.
+ * tspgnn_apply_gradients: model.py:160-167: adds l2norm_scaling * var (gradient of the L2 term),
+ *                        clip_by_global_norm(0.65), one Adam step (lr 2e-5, TF defaults), then
+ *                        refreshes every derived operand image.  Synchronises `stream`.
+ * tspgnn_train_step_host: all of the above with host buffers; loss / logits / predictions are the
+ *                        values computed with the variables BEFORE the update, like the reference's
+ *                        single sess.run. */
+int tspgnn_train_forward(tspgnn_handle h, const float* dW, const float* dC, int time_steps, float* d_logits,
+                         float* d_predictions, void* stream);
+int tspgnn_backward(tspgnn_handle h, const float* d_route_exists, int global_batch, float* d_grads, float* d_loss,
+                    void* stream);
+int tspgnn_apply_gradients(tspgnn_handle h, float* d_grads, float* host_global_norm, void* stream);
+int tspgnn_train_step_host(tspgnn_handle h, const float* W, const float* C, const float* route_exists, int time_steps,
+                           float* loss, float* logits, float* predictions, void* stream);
+float* tspgnn_grad_buffer(tspgnn_handle h);
+
+/* Current value of every trainable variable (host blob, tspgnn_param_count floats): what
+ * util.save_weights persists (util.py:24-37). */
+int tspgnn_get_params(tspgnn_handle h, float* host_blob, int64_t n_floats);
+
+/* Hyper-parameters of model.py:13-15 and tf.train.AdamOptimizer (defaults: 2e-5, 1e-10, 0.65,
+ * 0.9, 0.999, 1e-8), and the Adam slots tf.train.Saver stores next to the variables (util.py:35). */
+int tspgnn_set_hyper(tspgnn_handle h, float learning_rate, float l2norm_scaling, float clip_norm, float beta1,
+                     float beta2, float epsilon);
+int tspgnn_get_optimizer_state(tspgnn_handle h, float* host_m, float* host_v, int64_t* step, int64_t n_floats);
+int tspgnn_set_optimizer_state(tspgnn_handle h, const float* host_m, const float* host_v, int64_t step,
+                               int64_t n_floats);
+
 /* Sizes of the current plan. */
 int64_t tspgnn_sum_edges(tspgnn_handle h);
 int64_t tspgnn_sum_vertices(tspgnn_handle h);

@@ -156,8 +156,9 @@ def test_session_drop_in_surface_with_dense_ev():
         loss, acc, preds, TP, FP, TN, FN = sess.run(
             [GNN["loss"], GNN["acc"], GNN["predictions"], GNN["TP"], GNN["FP"], GNN["TN"], GNN["FN"]], feed_dict=feed)
         states = sess.run(GNN["last_states"], feed_dict=feed)
-        with pytest.raises(NotImplementedError):
-            sess.run(GNN["train_step"], feed_dict=feed)
+        no_label = {k: v for k, v in feed.items() if k is not GNN["route_exists"]}
+        with pytest.raises(ValueError, match="route_exists"):
+            sess.run(GNN["train_step"], feed_dict=no_label)      # the training step needs labels
     ref = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, 5)
     m = orc.metrics(ref["logits"], y)
     assert np.abs(preds - ref["predictions"]).max() <= 1e-4

@@ -45,6 +45,22 @@ SIGNATURES = [
                                           ctypes.POINTER(ctypes.c_float), ctypes.c_void_p]),
     ("tspgnn_debug_timeline", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                              ctypes.c_void_p]),
+    ("tspgnn_train_forward", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    ("tspgnn_backward", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p]),
+    ("tspgnn_apply_gradients", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float),
+                                              ctypes.c_void_p]),
+    ("tspgnn_train_step_host", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p]),
+    ("tspgnn_grad_buffer", ctypes.c_void_p, [ctypes.c_void_p]),
+    ("tspgnn_get_params", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
+    ("tspgnn_set_hyper", ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_float] * 6),
+    ("tspgnn_get_optimizer_state", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                  ctypes.POINTER(ctypes.c_int64), ctypes.c_int64]),
+    ("tspgnn_set_optimizer_state", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                  ctypes.c_int64]),
     ("tspgnn_dense_ev_to_coo", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                               ctypes.c_void_p, ctypes.c_void_p]),
 ]

@@ -1,0 +1,464 @@
+// fp32 CUDA-core kernels of the training step (model.py:157-167): the reverse pass through the
+// message-passing loop, the vote / initial-embedding MLPs, and the optimizer.
+//
+// The reverse pass recomputes each timestep's intermediates from the (h, c) snapshots the training
+// forward keeps, so it is built from a few generic pieces on row-major fp32 [rows, 64*k] matrices:
+//   rowgemm_kernel   Y = epi(X . W (+ b))           X in 64-column blocks, W or W^T resident in smem
+//   xtdy_kernel      dW += X^T . dY, db += colsum(dY)   (reduction over rows, fp32 atomics)
+//   lstm_bwd_kernel  reverse of the LayerNorm-LSTM gate math, one warp per row
+//   gather2 / scatter2   EV . y  and  EV^T . y  for the two non-zeros of every edge row
+// All matrices are addressed as (pointer, leading dimension); rows >= n_rows are never touched.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace tspgnn {
+
+constexpr int RG_THREADS = 256;            // rows per tile of rowgemm (thread = row)
+constexpr int RG_XLD = RG_THREADS + 1;     // transposed staging [k][row]
+constexpr int RG_MAXB = 4;                 // up to 4 blocks of 64 columns on either side
+
+struct RowGemmArgs {
+  const float* x[RG_MAXB];   // input column block kb: x[kb][row * xld[kb] + 0..63]
+  int xld[RG_MAXB];
+  float* y[RG_MAXB];         // output column block nb
+  int yld[RG_MAXB];
+  const float* w;            // stored matrix Ws[i * ldw + j], valid for i < w_rows, j < w_cols (else 0)
+  int ldw, w_rows, w_cols;
+  const float* bias;         // [N] (first bias_n valid) or nullptr
+  int bias_n;
+  const float* mask;         // EPI_MASK: multiply by (mask[row * mld + col] > 0); one 64-column block (N == 64)
+  int mld;
+  int64_t n_rows;
+};
+
+constexpr int EPI_NONE = 0, EPI_RELU = 1, EPI_MASK = 2, EPI_ACCUM = 4;
+
+__host__ __device__ constexpr int rowgemm_smem_bytes(int K, int N) { return (K * N + 64 * RG_XLD) * 4; }
+
+// Y[r, n] = epi( sum_k X[r, k] * Wm[k, n] + bias[n] ),  K = 64*KB, N = 64*NB.
+// TRANS = false: Wm[k, n] = Ws[k, n];  TRANS = true: Wm[k, n] = Ws[n, k]  (dX = dY . W^T).
+// EPI flags: RELU, MASK (zero where the forward activation was not positive), ACCUM (Y += ...).
+template <int KB, int NB, bool TRANS, int EPI>
+__global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a) {
+  extern __shared__ float smem[];
+  constexpr int K = 64 * KB, N = 64 * NB;
+  float* Wm = smem;              // [K][N]
+  float* xs = smem + K * N;      // [64][RG_XLD]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * N; i += RG_THREADS) {
+    const int k = i / N, n = i % N;
+    const int wi = TRANS ? n : k, wj = TRANS ? k : n;
+    Wm[i] = (wi < a.w_rows && wj < a.w_cols) ? a.w[static_cast<int64_t>(wi) * a.ldw + wj] : 0.f;
+  }
+  const int64_t n_tiles = (a.n_rows + RG_THREADS - 1) / RG_THREADS;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * RG_THREADS;
+#pragma unroll 1
+    for (int nb = 0; nb < NB; ++nb) {
+      float acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = (a.bias != nullptr && nb * 64 + j < a.bias_n) ? a.bias[nb * 64 + j] : 0.f;
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        __syncthreads();   // previous users of xs (and the weight load) are done
+        const float* xp = a.x[kb];
+        const int xld = a.xld[kb];
+        for (int i = tid; i < RG_THREADS * 64; i += RG_THREADS) {
+          const int r = i >> 6, k = i & 63;
+          xs[k * RG_XLD + r] = (row0 + r < a.n_rows) ? xp[(row0 + r) * xld + k] : 0.f;
+        }
+        __syncthreads();
+        const float* Wk = Wm + (kb * 64) * N + nb * 64;
+#pragma unroll 2
+        for (int k = 0; k < 64; ++k) {
+          const float xv = xs[k * RG_XLD + tid];
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 w = *reinterpret_cast<const float4*>(Wk + k * N + j4 * 4);
+            acc[j4 * 4 + 0] = fmaf(xv, w.x, acc[j4 * 4 + 0]);
+            acc[j4 * 4 + 1] = fmaf(xv, w.y, acc[j4 * 4 + 1]);
+            acc[j4 * 4 + 2] = fmaf(xv, w.z, acc[j4 * 4 + 2]);
+            acc[j4 * 4 + 3] = fmaf(xv, w.w, acc[j4 * 4 + 3]);
+          }
+        }
+      }
+      __syncthreads();   // everyone is done reading xs as the X operand
+#pragma unroll
+      for (int j = 0; j < 64; ++j) xs[j * RG_XLD + tid] = (EPI & EPI_RELU) ? fmaxf(acc[j], 0.f) : acc[j];
+      __syncthreads();
+      float* yp = a.y[nb];
+      const int yld = a.yld[nb];
+      for (int i = tid; i < RG_THREADS * 64; i += RG_THREADS) {
+        const int r = i >> 6, j = i & 63;
+        if (row0 + r < a.n_rows) {
+          float v = xs[j * RG_XLD + r];
+          if (EPI & EPI_MASK) v = (a.mask[(row0 + r) * a.mld + j] > 0.f) ? v : 0.f;
+          float* dst = yp + (row0 + r) * yld + j;
+          if (EPI & EPI_ACCUM) v += *dst;
+          *dst = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// dW[kb*64 + k, nb*64 + n] += sum_r X[r, kb*64 + k] * dY[r, nb*64 + n]      (blockIdx.y = kb, blockIdx.z = nb)
+// db[nb*64 + n]            += sum_r dY[r, nb*64 + n]                          (only the kb == 0 CTAs)
+// 256 threads, each a 4x4 block of the 64x64 tile; rows are streamed 32 at a time through shared memory.
+// ------------------------------------------------------------------------------------
+struct XtdyArgs {
+  const float* x[RG_MAXB];
+  int xld[RG_MAXB];
+  const float* dy;      // dY[row * dyld + nb*64 + n]
+  int dyld;
+  float* dw;            // dW[i * ldw + j], only i < w_rows, j < w_cols are written
+  int ldw, w_rows, w_cols;
+  float* db;            // nullptr or [w_cols]
+  int64_t n_rows;
+};
+
+constexpr int XT_ROWS = 32;
+
+__global__ void __launch_bounds__(256) xtdy_kernel(const XtdyArgs a) {
+  __shared__ __align__(16) float Xs[XT_ROWS][64];
+  __shared__ __align__(16) float Ys[XT_ROWS][64];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int kb = blockIdx.y, nb = blockIdx.z;
+  const float* xp = a.x[kb];
+  const int xld = a.xld[kb];
+  const float* yp = a.dy + nb * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool do_bias = (a.db != nullptr) && kb == 0 && ty == 0;
+  const int64_t n_chunks = (a.n_rows + XT_ROWS - 1) / XT_ROWS;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t row0 = ch * XT_ROWS;
+    __syncthreads();
+    // 32 rows x 16 float4 per matrix = 512 float4 each; two per thread and matrix
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * 256;
+      const int r = i >> 4, c4 = i & 15;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv;
+      if (row0 + r < a.n_rows) {
+        xv = *reinterpret_cast<const float4*>(xp + (row0 + r) * xld + c4 * 4);
+        yv = *reinterpret_cast<const float4*>(yp + (row0 + r) * a.dyld + c4 * 4);
+      }
+      *reinterpret_cast<float4*>(&Xs[r][c4 * 4]) = xv;
+      *reinterpret_cast<float4*>(&Ys[r][c4 * 4]) = yv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < XT_ROWS; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(&Xs[r][ty * 4]);
+      const float4 yv = *reinterpret_cast<const float4*>(&Ys[r][tx * 4]);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
+      if (do_bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bs[j] += ya[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int wi = kb * 64 + ty * 4 + i, wj = nb * 64 + tx * 4 + j;
+      if (wi < a.w_rows && wj < a.w_cols) atomicAdd(a.dw + static_cast<int64_t>(wi) * a.ldw + wj, acc[i][j]);
+    }
+  if (do_bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int wj = nb * 64 + tx * 4 + j;
+      if (wj < a.w_cols) atomicAdd(a.db + wj, bs[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Reverse of the LayerNorm-LSTM gate math, one warp per row, lane = columns
+// lane and lane + 32 of every gate.
+//   in : z [rows,256] pre-LayerNorm gates (recomputed), c_prev, g_h = dL/dh', g_c = dL/dc'
+//   out: z  <- dL/dz (in place),  g_c <- dL/dc_prev (in place),
+//        grad blob: += dL/dgamma, dL/dbeta of the five LayerNorms (fp32 atomics)
+// ------------------------------------------------------------------------------------
+struct LnOffsets {
+  int gamma[5], beta[5];   // offsets into the parameter / gradient blob; order input, transform, forget, output, state
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// forward LayerNorm statistics of a 64-vector held as 2 values per lane: uh = (u - mean) * r
+__device__ __forceinline__ void ln_fwd2(const float (&u)[2], float (&uh)[2], float& r) {
+  const float mean = warp_sum(u[0] + u[1]) * (1.0f / 64.0f);
+  const float d0 = u[0] - mean, d1 = u[1] - mean;
+  const float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / 64.0f);
+  r = rsqrtf(var + LN_EPS);
+  uh[0] = d0 * r;
+  uh[1] = d1 * r;
+}
+
+// reverse of y = uh * gamma + beta: returns du, accumulates dgamma / dbeta
+__device__ __forceinline__ void ln_bwd2(const float (&dy)[2], const float (&uh)[2], float r, const float (&gamma)[2],
+                                        float (&du)[2], float (&dgam)[2], float (&dbet)[2]) {
+  dgam[0] += dy[0] * uh[0];
+  dgam[1] += dy[1] * uh[1];
+  dbet[0] += dy[0];
+  dbet[1] += dy[1];
+  const float a0 = dy[0] * gamma[0], a1 = dy[1] * gamma[1];
+  const float m1 = warp_sum(a0 + a1) * (1.0f / 64.0f);
+  const float m2 = warp_sum(a0 * uh[0] + a1 * uh[1]) * (1.0f / 64.0f);
+  du[0] = r * (a0 - m1 - uh[0] * m2);
+  du[1] = r * (a1 - m1 - uh[1] * m2);
+}
+
+__global__ void __launch_bounds__(256) lstm_bwd_kernel(float* __restrict__ z, const float* __restrict__ c_prev,
+                                                       const float* __restrict__ g_h, float* __restrict__ g_c,
+                                                       int64_t n_rows, const float* __restrict__ params,
+                                                       float* __restrict__ grads, const LnOffsets off) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  float gam[5][2], bet[5][2], dgam[5][2], dbet[5][2];
+#pragma unroll
+  for (int g = 0; g < 5; ++g)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      gam[g][q] = params[off.gamma[g] + lane + 32 * q];
+      bet[g][q] = params[off.beta[g] + lane + 32 * q];
+      dgam[g][q] = 0.f;
+      dbet[g][q] = 0.f;
+    }
+  for (int64_t row = warp; row < n_rows; row += n_warps) {
+    float zg[4][2], uh[4][2], r[4], c[2], gh[2], gc[2];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      zg[g][0] = z[row * 256 + g * 64 + lane];
+      zg[g][1] = z[row * 256 + g * 64 + lane + 32];
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      c[q] = c_prev[row * 64 + lane + 32 * q];
+      gh[q] = g_h[row * 64 + lane + 32 * q];
+      gc[q] = g_c[row * 64 + lane + 32 * q];
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ln_fwd2(zg[g], uh[g], r[g]);
+    float si[2], sf[2], so[2], jj[2], gg[2], ct[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      si[q] = sigmoidf_acc(uh[0][q] * gam[0][q] + bet[0][q]);
+      jj[q] = uh[1][q] * gam[1][q] + bet[1][q];
+      gg[q] = fmaxf(jj[q], 0.f);
+      sf[q] = sigmoidf_acc(uh[2][q] * gam[2][q] + bet[2][q] + FORGET_BIAS);
+      so[q] = sigmoidf_acc(uh[3][q] * gam[3][q] + bet[3][q]);
+      ct[q] = c[q] * sf[q] + si[q] * gg[q];
+    }
+    float ch[2], cr;
+    ln_fwd2(ct, ch, cr);
+    float d_so[2], d_cn[2], d_ct[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float cn = ch[q] * gam[4][q] + bet[4][q];
+      d_so[q] = gh[q] * fmaxf(cn, 0.f);
+      d_cn[q] = gc[q] + ((cn > 0.f) ? gh[q] * so[q] : 0.f);
+    }
+    ln_bwd2(d_cn, ch, cr, gam[4], d_ct, dgam[4], dbet[4]);
+    float dgate[4][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      g_c[row * 64 + lane + 32 * q] = d_ct[q] * sf[q];
+      dgate[0][q] = d_ct[q] * gg[q] * si[q] * (1.0f - si[q]);
+      dgate[1][q] = (jj[q] > 0.f) ? d_ct[q] * si[q] : 0.f;
+      dgate[2][q] = d_ct[q] * c[q] * sf[q] * (1.0f - sf[q]);
+      dgate[3][q] = d_so[q] * so[q] * (1.0f - so[q]);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float du[2];
+      ln_bwd2(dgate[g], uh[g], r[g], gam[g], du, dgam[g], dbet[g]);
+      z[row * 256 + g * 64 + lane] = du[0];
+      z[row * 256 + g * 64 + lane + 32] = du[1];
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 5; ++g)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      atomicAdd(grads + off.gamma[g] + lane + 32 * q, dgam[g][q]);
+      atomicAdd(grads + off.beta[g] + lane + 32 * q, dbet[g][q]);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// out[e, :] = in[src[e], :] + in[dst[e], :]    ( = EV . in, graphnn.py:156-160 )
+// 16 threads per row, one float4 each.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather2_kernel(const float* __restrict__ in, const int32_t* __restrict__ src,
+                                                      const int32_t* __restrict__ dst, int64_t n_rows,
+                                                      float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rows * 16) return;
+  const int64_t e = i >> 4;
+  const int c4 = static_cast<int>(i & 15);
+  const float4 u = reinterpret_cast<const float4*>(in + static_cast<int64_t>(src[e]) * 64)[c4];
+  const float4 w = reinterpret_cast<const float4*>(in + static_cast<int64_t>(dst[e]) * 64)[c4];
+  reinterpret_cast<float4*>(out + e * 64)[c4] = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+}
+
+// out[src[e], :] += in[e, :]; out[dst[e], :] += in[e, :]    ( = EV^T . in ); `out` must be zeroed first.
+// `in` has leading dimension ld.  16 threads per row, one red.global.add.v4.f32 per endpoint.
+__global__ void __launch_bounds__(256) scatter2_kernel(const float* __restrict__ in, int ld,
+                                                       const int32_t* __restrict__ src,
+                                                       const int32_t* __restrict__ dst, int64_t n_rows,
+                                                       float* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rows * 16) return;
+  const int64_t e = i >> 4;
+  const int c4 = static_cast<int>(i & 15);
+  const float4 v = *reinterpret_cast<const float4*>(in + e * ld + c4 * 4);
+  ptx::red_add_v4(out + static_cast<int64_t>(src[e]) * 64 + c4 * 4, v);
+  ptx::red_add_v4(out + static_cast<int64_t>(dst[e]) * 64 + c4 * 4, v);
+}
+
+// ------------------------------------------------------------------------------------
+// Loss (model.py:157) and its gradient with respect to the per-edge votes:
+//   loss = (1/Bg) sum_k max(l,0) - l*y + log1p(exp(-|l|));  dvote_k = (sigmoid(l_k) - y_k) / (Bg * n_edges[k])
+// Bg = global batch (the divisor of reduce_mean when instances are sharded over ranks).  One CTA.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ logits,
+                                                        const float* __restrict__ route_exists,
+                                                        const int64_t* __restrict__ eoff, int n_instances,
+                                                        float inv_global_batch, float* __restrict__ dvote_inst,
+                                                        float* __restrict__ loss) {
+  __shared__ float part[8];
+  float s = 0.f;
+  for (int k = threadIdx.x; k < n_instances; k += blockDim.x) {
+    const float l = logits[k], y = route_exists[k];
+    s += fmaxf(l, 0.f) - l * y + log1pf(expf(-fabsf(l)));
+    const float ne = static_cast<float>(eoff[k + 1] - eoff[k]);
+    dvote_inst[k] = (sigmoidf_acc(l) - y) * inv_global_batch / ne;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    *loss = t * inv_global_batch;
+  }
+}
+
+// Reverse of the 64->1 tail of E_vote (model.py:107-128): vote[e] = a3[e,:] . w4 + b4.
+//   d3[e, j] = dvote[inst(e)] * w4[j] * (a3[e, j] > 0);  dw4[j] += sum_e a3[e, j] dvote;  db4 += sum_e dvote
+// One warp per row (grid-stride), lane = columns lane, lane + 32.
+__global__ void __launch_bounds__(256) vote_tail_bwd_kernel(const float* __restrict__ a3,
+                                                            const float* __restrict__ dvote_inst,
+                                                            const int64_t* __restrict__ eoff, int n_instances,
+                                                            int64_t n_rows, const float* __restrict__ w4,
+                                                            float* __restrict__ d3, float* __restrict__ dw4,
+                                                            float* __restrict__ db4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const float w0 = w4[lane], w1 = w4[lane + 32];
+  float g0 = 0.f, g1 = 0.f, gb = 0.f;
+  for (int64_t row = warp; row < n_rows; row += n_warps) {
+    // instance of this row: largest k with eoff[k] <= row
+    int lo = 0, hi = n_instances - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (eoff[mid] <= row) lo = mid; else hi = mid - 1;
+    }
+    const float dv = dvote_inst[lo];
+    const float x0 = a3[row * 64 + lane], x1 = a3[row * 64 + lane + 32];
+    d3[row * 64 + lane] = (x0 > 0.f) ? dv * w0 : 0.f;
+    d3[row * 64 + lane + 32] = (x1 > 0.f) ? dv * w1 : 0.f;
+    g0 = fmaf(x0, dv, g0);
+    g1 = fmaf(x1, dv, g1);
+    gb += dv;
+  }
+  atomicAdd(dw4 + lane, g0);
+  atomicAdd(dw4 + lane + 32, g1);
+  if (lane == 0) atomicAdd(db4, gb);
+}
+
+// X0[e, :] = [W[e], C[e], 0, ...]  : the input of E_init_MLP (model.py:43) padded to 64 columns
+__global__ void __launch_bounds__(256) pad_wc_kernel(const float* __restrict__ W, const float* __restrict__ C,
+                                                     int64_t n_rows, float* __restrict__ X0) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rows * 64) return;
+  const int64_t e = i >> 6;
+  const int c = static_cast<int>(i & 63);
+  X0[i] = (c == 0) ? W[e] : (c == 1 ? C[e] : 0.f);
+}
+
+// dV_init[j] += sum_v gVh[v, j] / sqrt(d)     (V0 = tile(V_init / sqrt(d)), model.py:46-51)
+__global__ void __launch_bounds__(256) vinit_grad_kernel(const float* __restrict__ gVh, int64_t n_rows, float scale,
+                                                         float* __restrict__ dvinit) {
+  const int j = threadIdx.x & 63;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 6);
+  float s = 0.f;
+  for (int64_t r = r0; r < n_rows; r += static_cast<int64_t>(gridDim.x) * 4) s += gVh[r * 64 + j];
+  atomicAdd(dvinit + j, s * scale);
+}
+
+// ------------------------------------------------------------------------------------
+// Optimizer (model.py:160-167): g += l2 * var;  global norm;  clip;  Adam.
+// scal[0] = global norm of the (L2-augmented) gradient.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) grad_l2_norm_kernel(float* __restrict__ g, const float* __restrict__ p,
+                                                            int64_t n, float l2, float* __restrict__ scal) {
+  __shared__ float part[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = fmaf(l2, p[i], g[i]);
+    g[i] = v;
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = part[threadIdx.x];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) scal[0] = sqrtf(t);
+  }
+}
+
+// TF: clip_by_global_norm scales by clip / max(norm, clip);  AdamOptimizer._apply_dense:
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; var -= lr_t * m / (sqrt(v) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                   const float* __restrict__ scal, float clip, float lr_t, float b1,
+                                                   float b2, float eps) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float scale = clip / fmaxf(scal[0], clip);
+  const float gi = g[i] * scale;
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+}  // namespace tspgnn

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace tspgnn;
 
@@ -148,6 +149,22 @@ struct tspgnn_ctx {
   int clamp_cell[2] = {1, 1};   // per cell: logistic exponents of the i / f gates need clamping
   std::map<int, cudaGraphExec_t> step_graphs;
   int64_t plan_generation = 0;
+  // ---- training step (model.py:157-167) ----
+  struct WorkSet {     // row-major fp32 scratch of the reverse pass, [rows, 64] unless noted
+    float *xg = nullptr, *Z = nullptr /* [rows,256] */, *dx = nullptr, *A1 = nullptr, *A2 = nullptr, *A3 = nullptr,
+          *D0 = nullptr, *D1 = nullptr, *dm = nullptr, *gH = nullptr, *gC = nullptr;
+    int64_t cap = 0;
+  } wsE, wsV;
+  float* snap = nullptr;          // per-timestep snapshots kept by the training forward
+  int64_t snap_cap = 0;           // floats
+  int snap_T = -1;                // timesteps held (-1: no training forward since the last plan / update)
+  int64_t snap_generation = -1;
+  float *d_grads = nullptr, *d_adam_m = nullptr, *d_adam_v = nullptr, *d_scal = nullptr, *d_y = nullptr,
+        *d_dvote = nullptr;
+  int64_t cap_y = 0;
+  int64_t adam_step = 0;
+  float lr = 2e-5f, l2 = 1e-10f, clip = 0.65f;                 // model.py:13-15
+  float adam_b1 = 0.9f, adam_b2 = 0.999f, adam_eps = 1e-8f;    // tf.train.AdamOptimizer defaults
 };
 
 static tspgnn_ctx* g_const_owner = nullptr;
@@ -234,6 +251,14 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
                   h->vote, h->stateE, h->stateV, h->d_W, h->d_C, h->d_logits, h->d_preds};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (tspgnn_ctx::WorkSet* w : {&h->wsE, &h->wsV}) {
+    void* wp[] = {w->xg, w->Z, w->dx, w->A1, w->A2, w->A3, w->D0, w->D1, w->dm, w->gH, w->gC};
+    for (void* p : wp)
+      if (p) cudaFree(p);
+  }
+  void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote};
+  for (void* p : tp)
+    if (p) cudaFree(p);
   if (g_const_owner == h) g_const_owner = nullptr;
   delete h;
   return 0;
@@ -247,18 +272,20 @@ extern "C" int64_t tspgnn_launch_count(tspgnn_handle h) { return h ? h->launches
 // ------------------------------------------------------------------------------------
 // parameters
 // ------------------------------------------------------------------------------------
-extern "C" int tspgnn_set_params(tspgnn_handle h, const float* blob, int64_t n_floats) {
-  if (!h || !blob) return fail(TSPGNN_E_INVALID, "NULL handle or blob");
-  if (n_floats != h->po.total)
-    return fail(TSPGNN_E_INVALID, "parameter blob has %lld floats, expected %lld", (long long)n_floats,
-                (long long)h->po.total);
+// Derives everything the kernels consume from the fp32 blob in h->hparams: constant payloads,
+// clamp decisions and the tensor-core operand images.  `upload_blob` also (re)creates d_params
+// (false when the device copy is already current, i.e. after an optimizer update).
+static int install_params(tspgnn_ctx* h, bool upload_blob) {
+  const float* blob = h->hparams.data();
+  const int64_t n_floats = h->po.total;
   for (int64_t i = 0; i < n_floats; ++i)
     if (!std::isfinite(blob[i])) return fail(TSPGNN_E_INVALID, "parameter blob has a non-finite value at %lld", (long long)i);
   CUDA_TRY(cudaSetDevice(h->device));
   const ParamOffsets& o = h->po;
-  h->hparams.assign(blob, blob + n_floats);
-  if (dev_alloc(&h->d_params, n_floats)) return TSPGNN_E_CUDA;
-  CUDA_TRY(cudaMemcpy(h->d_params, blob, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+  if (upload_blob) {
+    if (dev_alloc(&h->d_params, n_floats)) return TSPGNN_E_CUDA;
+    CUDA_TRY(cudaMemcpy(h->d_params, blob, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+  }
   // constant payloads
   for (int c = 0; c < 2; ++c)
     for (int g = 0; g < 5; ++g) {
@@ -315,7 +342,7 @@ extern "C" int tspgnn_set_params(tspgnn_handle h, const float* blob, int64_t n_f
       for (int p = 0; p < hp; ++p)
         for (int kb = 0; kb < 2; ++kb)
           make_b_image(kc.data(), 4 * D, kb * 64, 0, 256, p, img.data() + (p * 2 + kb) * 32768);
-      if (dev_alloc(&h->d_wlstm[c], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
+      if (!h->d_wlstm[c] && dev_alloc(&h->d_wlstm[c], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
       CUDA_TRY(cudaMemcpy(h->d_wlstm[c], img.data(), img.size(), cudaMemcpyHostToDevice));
     }
     for (int m = 0; m < 3; ++m) {
@@ -324,12 +351,24 @@ extern "C" int tspgnn_set_params(tspgnn_handle h, const float* blob, int64_t n_f
       for (int l = 0; l < nl; ++l)
         for (int p = 0; p < hp; ++p)
           make_b_image(blob + (m == 2 ? o.vote_w[l] : o.msg_w[m][l]), D, 0, 0, 64, p, img.data() + (l * hp + p) * 8192);
-      if (dev_alloc(&h->d_wmlp[m], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
+      if (!h->d_wmlp[m] && dev_alloc(&h->d_wmlp[m], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
       CUDA_TRY(cudaMemcpy(h->d_wmlp[m], img.data(), img.size(), cudaMemcpyHostToDevice));
     }
   }
   h->has_params = true;
+  h->snap_T = -1;   // snapshots of a training forward belong to the previous parameters
   return 0;
+}
+
+extern "C" int tspgnn_set_params(tspgnn_handle h, const float* blob, int64_t n_floats) {
+  if (!h || !blob) return fail(TSPGNN_E_INVALID, "NULL handle or blob");
+  if (n_floats != h->po.total)
+    return fail(TSPGNN_E_INVALID, "parameter blob has %lld floats, expected %lld", (long long)n_floats,
+                (long long)h->po.total);
+  for (int64_t i = 0; i < n_floats; ++i)
+    if (!std::isfinite(blob[i])) return fail(TSPGNN_E_INVALID, "parameter blob has a non-finite value at %lld", (long long)i);
+  h->hparams.assign(blob, blob + n_floats);
+  return install_params(h, true);
 }
 
 // ------------------------------------------------------------------------------------
@@ -440,6 +479,7 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
   h->tilesV = static_cast<int>(nV_pad / TILE_ROWS);
   h->has_plan = true;
   h->plan_generation++;
+  h->snap_T = -1;
   return 0;
 }
 
@@ -561,13 +601,23 @@ static int simt_mlp(tspgnn_ctx* h, cudaStream_t s, const float* x, int64_t rows,
   return 0;
 }
 
-static int one_step(tspgnn_ctx* h, cudaStream_t s) {
+// First half of while_body (graphnn.py:152-161): both message MLPs and the EV^T product; leaves
+// mV (vertex messages) and xV (summed edge messages) for the cells.
+static int step_messages(tspgnn_ctx* h, cudaStream_t s) {
   if (h->hp == 0) {
     // graphnn.py:142-173, both variables read the time-t states
     if (simt_mlp(h, s, h->Eh, h->nE, 1, h->mE)) return TSPGNN_E_CUDA;
     if (simt_mlp(h, s, h->Vh, h->nV, 0, h->mV)) return TSPGNN_E_CUDA;
     simt_segment_sum_kernel<<<grid_for(h->nV * 32, 256), 256, 0, s>>>(h->mE, h->d_vptr, h->d_vidx, h->nV, h->xV);
     LAUNCH_CHECK(h);
+    return 0;
+  }
+  return (h->hp == 2) ? tc_launch_k2<2>(h, s, false) : tc_launch_k2<1>(h, s, false);
+}
+
+// Second half (graphnn.py:155-170): EV product (gather) + both LayerNorm-LSTM cells, in place.
+static int step_cells(tspgnn_ctx* h, cudaStream_t s) {
+  if (h->hp == 0) {
     const int smem = (2 * D * 4 * D + 2 * D * XS_LD) * 4;
     const int gv = std::max(1, std::min(h->num_sms, grid_for(h->nV, SIMT_THREADS)));
     simt_lnlstm_kernel<false><<<gv, SIMT_THREADS, smem, s>>>(h->xV, nullptr, nullptr, h->nV,
@@ -579,12 +629,12 @@ static int one_step(tspgnn_ctx* h, cudaStream_t s) {
     LAUNCH_CHECK(h);
     return 0;
   }
-  if (h->hp == 2) {
-    if (tc_launch_k2<2>(h, s, false)) return TSPGNN_E_CUDA;
-    return tc_launch_k1<2>(h, s);
-  }
-  if (tc_launch_k2<1>(h, s, false)) return TSPGNN_E_CUDA;
-  return tc_launch_k1<1>(h, s);
+  return (h->hp == 2) ? tc_launch_k1<2>(h, s) : tc_launch_k1<1>(h, s);
+}
+
+static int one_step(tspgnn_ctx* h, cudaStream_t s) {
+  if (step_messages(h, s)) return TSPGNN_E_CUDA;
+  return step_cells(h, s);
 }
 
 extern "C" int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const float* dC, void* stream) {
@@ -862,3 +912,5 @@ extern "C" int tspgnn_dense_ev_to_coo(const void* EV, int elem_size, int64_t row
   }
   return 0;
 }
+
+#include "train_host.inc"

@@ -119,6 +119,82 @@ class Engine(object):
         _lib.check(_lib.lib.tspgnn_set_states(self._h, *ptrs, self._sptr(s)))
         s.synchronize()
 
+    # -- training step (model.py:157-167) -------------------------------------------
+    def train_step_host(self, W, C, route_exists, time_steps, stream=None):
+        """One ``sess.run([train_step, loss, predictions])`` (train.py:35-42): host numpy in,
+        (loss, logits, predictions) of the pre-update variables out; the variables, Adam
+        slots and every derived operand image are updated on the device."""
+        W = np.ascontiguousarray(np.asarray(W, dtype=np.float32).reshape(-1))
+        C = np.ascontiguousarray(np.asarray(C, dtype=np.float32).reshape(-1))
+        y = np.ascontiguousarray(np.asarray(route_exists, dtype=np.float32).reshape(-1))
+        if W.shape[0] != self.n_edges_total or C.shape[0] != self.n_edges_total:
+            raise ValueError("W and C must have sum(n_edges)=%d rows" % self.n_edges_total)
+        if y.shape[0] != self.B:
+            raise ValueError("route_exists must have one entry per instance (%d)" % self.B)
+        loss = ctypes.c_float(0)
+        logits = np.empty(self.B, dtype=np.float32)
+        preds = np.empty(self.B, dtype=np.float32)
+        _lib.check(_lib.lib.tspgnn_train_step_host(self._h, _np_ptr(W), _np_ptr(C), _np_ptr(y), int(time_steps),
+                                                   ctypes.byref(loss), _np_ptr(logits), _np_ptr(preds),
+                                                   self._sptr(stream)))
+        return float(loss.value), logits, preds
+
+    def train_forward(self, dW, dC, time_steps, d_logits=None, d_preds=None, stream=None):
+        """Forward pass that keeps the per-timestep state the reverse pass needs (device tensors)."""
+        _lib.check(_lib.lib.tspgnn_train_forward(
+            self._h, ctypes.c_void_p(dW.data_ptr()), ctypes.c_void_p(dC.data_ptr()), int(time_steps),
+            ctypes.c_void_p(d_logits.data_ptr()) if d_logits is not None else None,
+            ctypes.c_void_p(d_preds.data_ptr()) if d_preds is not None else None, self._sptr(stream)))
+
+    def backward(self, d_route_exists, global_batch=0, stream=None):
+        """Loss and flat gradient blob (device tensors) of the last train_forward.  ``global_batch``
+        is the divisor of the loss mean; with instances sharded over ranks pass the size of the
+        whole batch and sum (all-reduce) the returned blobs."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        s = stream if stream is not None else self.stream()
+        with torch.cuda.stream(s):
+            grads = torch.empty(self.param_count, dtype=torch.float32, device=dev)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.tspgnn_backward(self._h, ctypes.c_void_p(d_route_exists.data_ptr()), int(global_batch),
+                                            ctypes.c_void_p(grads.data_ptr()), ctypes.c_void_p(loss.data_ptr()),
+                                            self._sptr(s)))
+        return loss, grads
+
+    def apply_gradients(self, d_grads, stream=None):
+        """L2 term + clip_by_global_norm + Adam (model.py:160-167); returns the global norm."""
+        norm = ctypes.c_float(0)
+        _lib.check(_lib.lib.tspgnn_apply_gradients(self._h, ctypes.c_void_p(d_grads.data_ptr()), ctypes.byref(norm),
+                                                   self._sptr(stream)))
+        return float(norm.value)
+
+    @property
+    def param_count(self):
+        return int(_lib.lib.tspgnn_param_count(self.d))
+
+    def get_params(self):
+        """Current variables as a flat float32 blob (params.unflatten turns it into a dict)."""
+        blob = np.empty(self.param_count, dtype=np.float32)
+        _lib.check(_lib.lib.tspgnn_get_params(self._h, _np_ptr(blob), blob.size))
+        return blob
+
+    def set_hyper(self, learning_rate=2e-5, l2norm_scaling=1e-10, clip_norm=0.65, beta1=0.9, beta2=0.999,
+                  epsilon=1e-8):
+        _lib.check(_lib.lib.tspgnn_set_hyper(self._h, learning_rate, l2norm_scaling, clip_norm, beta1, beta2, epsilon))
+
+    def get_optimizer_state(self):
+        n = self.param_count
+        m = np.empty(n, dtype=np.float32)
+        v = np.empty(n, dtype=np.float32)
+        step = ctypes.c_int64(0)
+        _lib.check(_lib.lib.tspgnn_get_optimizer_state(self._h, _np_ptr(m), _np_ptr(v), ctypes.byref(step), n))
+        return {"m": m, "v": v, "step": int(step.value)}
+
+    def set_optimizer_state(self, state):
+        m = np.ascontiguousarray(state["m"], dtype=np.float32)
+        v = np.ascontiguousarray(state["v"], dtype=np.float32)
+        _lib.check(_lib.lib.tspgnn_set_optimizer_state(self._h, _np_ptr(m), _np_ptr(v), int(state["step"]), m.size))
+
     def time_kernel(self, which, iters, stream=None):
         """Mean device time (ms) of one launch of K1 (which=0) or K2 (which=1)."""
         ms = ctypes.c_float(0)

@@ -13,7 +13,9 @@ the reference run unchanged against the CUDA engine (model.py:9-171, train.py:17
                        GNN['route_exists']: y, GNN['n_vertices']: nv, GNN['n_edges']: ne})
 
 ``EV`` may be the reference's dense ``[sumE,sumV]`` array or an ``instances.Incidence``.
-``train_step`` is declared but raises: the backward pass is outside this round's scope.
+Fetching ``train_step`` runs the reverse pass, the L2 term, the global-norm clip and one Adam
+step on the device (model.py:157-167); the other fetches of the same ``run`` are the values of
+the pre-update variables, as in the reference's single ``sess.run``.
 """
 import numpy as np
 
@@ -51,7 +53,7 @@ def global_variables_initializer(seed=None):
 
 
 def build_network(d, mode="bf16x3", device=0):
-    # hyper-parameters of model.py:13-15 (used by the training step, not built yet)
+    # hyper-parameters of model.py:13-15
     learning_rate = 2e-5
     l2norm_scaling = 1e-10
     global_norm_gradient_clipping_ratio = 0.65
@@ -123,6 +125,7 @@ class Session(object):
         self._gnn = GNN
         self._engine = None
         self._params = None
+        self._params_stale = False      # the device holds newer variables than self._params
         self._plan_key = None
 
     def __enter__(self):
@@ -143,21 +146,33 @@ class Session(object):
             from .engine import Engine
             cfg = self._gnn["_config"]
             self._engine = Engine(cfg["d"], cfg["mode"], cfg["device"])
+            self._engine.set_hyper(cfg["learning_rate"], cfg["l2norm_scaling"], cfg["clip"])
             self._gnn["gnn"].bind(self._engine)
         return self._engine
 
     def set_variables(self, params):
         self._params = {k: np.asarray(v, dtype=np.float32) for k, v in params.items()}
+        self._params_stale = False
         self._ensure_engine().set_params(self._params)
 
     def get_variables(self):
+        if self._params_stale:
+            self._params = _params.unflatten(self._engine.get_params(), self._gnn["_config"]["d"])
+            self._params_stale = False
         return dict(self._params)
+
+    def get_optimizer_state(self):
+        """Adam slots + step (tf.train.Saver stores them with the variables, util.py:35)."""
+        return self._ensure_engine().get_optimizer_state()
+
+    def set_optimizer_state(self, state):
+        self._ensure_engine().set_optimizer_state(state)
 
     def load_weights(self, path):
         self.set_variables(_params.load_weights(path))
 
     def save_weights(self, path):
-        _params.save_weights(self._params, path)
+        _params.save_weights(self.get_variables(), path)
 
     # -- run ------------------------------------------------------------------------
     def run(self, fetches, feed_dict=None):
@@ -172,8 +187,7 @@ class Session(object):
         for k, v in (feed_dict or {}).items():
             feed[k.name if isinstance(k, Placeholder) else str(k)] = v
         names = [f.name for f in flist]
-        if "train_step" in names:
-            raise NotImplementedError("train_step (backward pass + Adam, model.py:157-167) is not built yet")
+        train = "train_step" in names
         if self._params is None:
             raise RuntimeError("Attempting to use uninitialized variables: run global_variables_initializer() "
                                "or load_weights() first")
@@ -200,8 +214,14 @@ class Session(object):
         if key != self._plan_key:
             eng.plan(nv, ne, EV.src, EV.dst)
             self._plan_key = key
-        logits, preds = eng.forward_host(W, C, int(feed["time_steps"]))
-        out = {"predictions": preds, "logits": logits}
+        if train:
+            if "route_exists" not in feed:
+                raise ValueError("You must feed a value for placeholder 'route_exists'")
+            _, logits, preds = eng.train_step_host(W, C, feed["route_exists"], int(feed["time_steps"]))
+            self._params_stale = True
+        else:
+            logits, preds = eng.forward_host(W, C, int(feed["time_steps"]))
+        out = {"predictions": preds, "logits": logits, "train_step": None}
         if any(n in names for n in ("TP", "FP", "TN", "FN", "acc", "loss")):
             if "route_exists" not in feed:
                 raise ValueError("You must feed a value for placeholder 'route_exists'")
