@@ -120,34 +120,46 @@ def test_sharded_gradients_add_up():
     assert np.abs(acc - g_full).max() <= 1e-4 * np.abs(g_full).max()
 
 
-def test_train_steps_follow_the_oracle_trajectory():
-    """Three optimizer steps on a fixed batch: losses, global norm and updated variables."""
+def test_optimizer_steps_match_oracle():
+    """Three optimizer steps on a fixed batch.  Adam's update lr * m / (sqrt(v) + eps) is sign-like for
+    the first steps, so free-running trajectories separate chaotically; every step is therefore
+    checked on its own: the oracle starts from the variables and Adam slots the device holds."""
     from tsp_gnn_b200.engine import Engine
     EV, W, C, y, nv, ne = inst.synth_batch([12, 15, 10, 13], seed=8)
-    params = orc.init_params(64, seed=4)
-    lr = 1e-3        # larger than the reference's 2e-5 so that three steps move the loss visibly
+    lr = 1e-3
     eng = Engine(64, "bf16x3", 0)
-    eng.set_params(params)
+    eng.set_params(orc.init_params(64, seed=4))
     eng.set_hyper(learning_rate=lr)
     eng.plan(nv, ne, EV.src, EV.dst)
-    cur = {k: v.astype(np.float64) for k, v in params.items()}
-    st = og.new_optimizer_state(cur)
+    names = [n for n, _, _ in P.param_spec(64)]
     for step in range(3):
+        cur = {k: v.astype(np.float64) for k, v in P.unflatten(eng.get_params()).items()}
+        opt = eng.get_optimizer_state()
+        assert opt["step"] == step
+        st = dict(step=opt["step"], m={k: v.astype(np.float64) for k, v in P.unflatten(opt["m"]).items()},
+                  v={k: v.astype(np.float64) for k, v in P.unflatten(opt["v"]).items()})
         loss, logits, preds = eng.train_step_host(W, C, y, 16)
         ref = og.forward_backward(cur, EV.src, EV.dst, W, C, nv, ne, y, 16)
-        cur, gnorm = og.apply_gradients(cur, ref["grads"], st, lr=lr)
-        print("step %d loss cuda %.7f oracle %.7f" % (step, loss, ref["loss"]))
-        assert abs(loss - ref["loss"]) < 2e-5
+        new, gnorm = og.apply_gradients(cur, ref["grads"], st, lr=lr)
+        print("step %d loss cuda %.7f oracle %.7f  |g| %.4f" % (step, loss, ref["loss"], gnorm))
+        assert abs(loss - ref["loss"]) < 1e-5
+        assert np.abs(preds - ref["predictions"]).max() < 1e-4
+        after = eng.get_optimizer_state()
+        m_ref = P.flatten({k: st["m"][k].astype(np.float32) for k in names}).astype(np.float64)
+        v_ref = P.flatten({k: st["v"][k].astype(np.float32) for k in names}).astype(np.float64)
+        # the moments are linear / quadratic in the clipped gradient
+        assert np.abs(after["m"] - m_ref).max() <= 5e-2 * np.abs(m_ref).max()
+        assert np.abs(after["v"] - v_ref).max() <= 1e-1 * np.abs(v_ref).max()
+        cos = float(np.dot(after["m"], m_ref) / (np.linalg.norm(after["m"]) * np.linalg.norm(m_ref)))
+        assert cos > 0.9999, cos
         got = P.unflatten(eng.get_params())
-        # Adam's step is lr * m / (sqrt(v) + eps): where |g| ~ eps = 1e-8 it is ill-conditioned, so the
-        # bulk of the variables is gated tightly and every variable loosely
-        diffs = np.concatenate([np.abs(got[k] - cur[k]).reshape(-1) for k in cur])
-        assert np.quantile(diffs, 0.99) < 0.05 * lr * (step + 1)
-        assert diffs.max() < 2.5 * lr * (step + 1)
-    opt = eng.get_optimizer_state()
-    assert opt["step"] == 3
-    m_ref = P.flatten({k: v.astype(np.float32) for k, v in st["m"].items()})
-    assert np.abs(opt["m"] - m_ref).max() <= 5e-3 * np.abs(m_ref).max()
+        # the update amplifies absolute gradient differences of 1e-7 where |g| is below ~1e-5: the bulk
+        # of the variables is gated tightly, all of them loosely (one step cannot exceed ~lr / (1 - b1))
+        diffs = np.concatenate([np.abs(got[k] - new[k]).reshape(-1) for k in names])
+        print("step %d |dvar| quantiles 50/90/99/100 %%: %s (lr %.0e)" %
+              (step, np.quantile(diffs, [0.5, 0.9, 0.99, 1.0]), lr))
+        assert np.quantile(diffs, 0.9) < 0.05 * lr
+        assert diffs.max() < 2.5 * lr
     eng.close()
 
 
@@ -156,7 +168,7 @@ def test_session_train_step_surface_and_loss_decreases(tmp_path):
     from tsp_gnn_b200 import build_network, Session, global_variables_initializer
     EV, W, C, y, nv, ne = inst.synth_batch([10, 12, 9, 11], seed=21)
     GNN = build_network(64)
-    GNN["_config"]["learning_rate"] = 2e-3
+    GNN["_config"]["learning_rate"] = 2e-4   # 10x the reference so that 20 steps move the loss
     feed = {GNN["EV"]: EV.toarray(), GNN["W"]: W.reshape(-1, 1), GNN["C"]: C.reshape(-1, 1),
             GNN["time_steps"]: 8, GNN["route_exists"]: y, GNN["n_vertices"]: nv, GNN["n_edges"]: ne}
     outputs = [GNN[k] for k in ("train_step", "loss", "acc", "predictions", "TP", "FP", "TN", "FN")]
@@ -164,14 +176,14 @@ def test_session_train_step_surface_and_loss_decreases(tmp_path):
         sess.run(global_variables_initializer(seed=3))
         before = sess.get_variables()
         losses = []
-        for _ in range(12):
+        for _ in range(20):
             res = sess.run(outputs, feed_dict=feed)
             loss, acc, predictions, TP, FP, TN, FN = res[-7:]
             assert res[0] is None and predictions.shape == (4,)
             assert TP + FP + TN + FN == 4
             losses.append(float(loss))
         after = sess.get_variables()
-        assert losses[-1] < losses[0] - 1e-3, losses
+        assert losses[-1] < losses[0] - 0.02, losses
         assert any(np.abs(after[k] - before[k]).max() > 0 for k in after)
         # checkpoint round trip incl. the Adam slots (util.py:24-37 saves every global variable)
         sess.save_weights(str(tmp_path / "ckpt"))
@@ -181,7 +193,7 @@ def test_session_train_step_surface_and_loss_decreases(tmp_path):
         sess2.load_weights(str(tmp_path / "ckpt"))
         sess2.set_optimizer_state(opt)
         assert abs(float(sess2.run(GNN["loss"], feed_dict=feed)) - eval_loss) < 1e-6
-        assert sess2.get_optimizer_state()["step"] == 12
+        assert sess2.get_optimizer_state()["step"] == 20
 
 
 def test_backward_requires_a_training_forward():
