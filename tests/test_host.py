@@ -193,6 +193,53 @@ def test_world_size_2_gloo_logit_allreduce(tmp_path):
     assert "GLOO_OK 2" in res.stdout
 
 
+_GLOO_GRAD_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import torch
+import torch.distributed as dist
+from tsp_gnn_b200 import sharding, params as P
+from tsp_gnn_b200 import instances as inst
+from oracle import tspgnn_oracle as orc, tspgnn_oracle_grad as og
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+EV, W, C, y, nv, ne = inst.synth_batch([5, 7, 6, 8, 5], seed=3)
+params = orc.init_params(64, seed=2)
+parts = sharding.partition_instances(ne, world)
+src, dst, w, c, nvl, nel = sharding.take_instances(parts[rank], EV.src, EV.dst, W, C, nv, ne)
+# the oracle stands in for the per-rank GPU engine: this test covers the sharding / reduction logic
+r = og.forward_backward(params, src, dst, w, c, nvl, nel, np.asarray(y)[parts[rank]], 3, global_batch=len(ne))
+blob = torch.from_numpy(P.flatten({{k: v.astype(np.float32) for k, v in r["grads"].items()}}))
+loss = torch.tensor([r["loss"]], dtype=torch.float32)
+sharding.all_reduce_gradients(blob, loss)
+full = og.forward_backward(params, EV.src, EV.dst, W, C, nv, ne, y, 3)
+ref = P.flatten({{k: v.astype(np.float32) for k, v in full["grads"].items()}})
+assert abs(float(loss[0]) - full["loss"]) < 1e-6
+assert np.abs(blob.numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+# every rank applies the same reduced gradient: replicas stay identical
+new, _ = og.apply_gradients(params, P.unflatten(blob.numpy()), og.new_optimizer_state(params))
+mine = torch.from_numpy(P.flatten({{k: v.astype(np.float32) for k, v in new.items()}}))
+other = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(other, mine)
+assert all(torch.equal(o, mine) for o in other)
+if rank == 0:
+    print("GLOO_GRAD_OK", world)
+dist.destroy_process_group()
+"""
+
+
+def test_world_size_2_gloo_gradient_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_GRAD_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "GLOO_GRAD_OK 2" in res.stdout
+
+
 def test_library_exports_every_declared_symbol():
     from tsp_gnn_b200 import _lib
     header = open(os.path.join(ROOT, "include", "tspgnn.h")).read()

@@ -59,6 +59,10 @@ struct K1Args {
   int64_t nE, nV;
   int tilesE, tilesV, e_ctas;
   int clampE, clampV;    // 1: clamp the logistic exponents of the i / f gates (large LayerNorm gamma / beta)
+  // Folded E_msg_V output layer (see K2Args::fold): xV then holds sum_e a3[e] (the last HIDDEN activations
+  // of the incident edges), wV is the image of [W4.Kx ; Kh] and the V epilogue adds deg(v) * (b4.Kx),
+  // c_vfold_bias, to z before the gate LayerNorms.  nullptr = unfolded.
+  const float* vdeg;     // [sumV_pad] number of incident edges of every vertex row
   long long* timeline;   // optional clock64() trace (tools/timeline.py), nullptr in production
 };
 
@@ -75,8 +79,16 @@ struct K2Args {
   int64_t nE, nV;
   int tilesE, tilesV, e_ctas;
   int vote_mode;
+  // fold = 1: the last (linear) layer of E_msg_V is not applied per edge.  Since
+  //   sum_{e in inc(v)} (a3[e].W4 + b4) = (sum_e a3[e]).W4 + deg(v).b4          (graphnn.py:152-161)
+  // edge tiles run three layers, scatter the hidden activations a3, and the vertex cell applies
+  // W4 (merged into its LSTM kernel) once per vertex instead of once per edge (K1Args::vdeg).
+  int fold;
   long long* timeline;
 };
+
+// (b4 of E_msg_V) . Kx of the V cell, centred per gate like the weight image (K1Args::vdeg)
+__constant__ float c_vfold_bias[4 * D];
 
 // timeline slot: [cta][role 0..3][local tile 0..63][event 0..7]
 constexpr int TL_ROLES = 4, TL_TILES = 64, TL_EVENTS = 8;
@@ -387,7 +399,8 @@ __device__ __forceinline__ float2 one_plus_ex2(float2 t) {
 
 template <int HP, int CELL, bool CLAMP>
 __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
-                                            uint64_t* acc_empty, int warp, int lane, long long* tl_, uint32_t ln_s) {
+                                            uint64_t* acc_empty, int warp, int lane, long long* tl_, uint32_t ln_s,
+                                            const float* __restrict__ vdeg) {
   // ln_s: shared-memory copy of this cell's LayerNorm parameters, gamma[g][j] at ln_s + (g*64+j)*4,
   // beta at +1280.  (Run-time indexed constant-bank loads cost ~10 cycles each; a broadcast
   // LDS.128 brings four values in ~2.)
@@ -411,6 +424,26 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
     ptx::mbar_wait(&acc_full[e], use & 1);
     tl_mark(tl, e, n, 1);
     ptx::tcgen05_fence_after();
+
+    if (CELL == 0 && vdeg != nullptr) {
+      // folded E_msg_V output layer: z += deg(v) * (b4 . Kx)   (vertex tiles only, 5 % of the rows).
+      // Fully unrolled so that the bias values are constant-bank operands of the FMAs.
+      const float dg = vdeg[static_cast<int64_t>(t0 + n) * TILE_ROWS + r];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float zz[64];
+        ptx::tmem_ld64(t_acc + g * 64, zz);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) zz[i] = fmaf(dg, c_vfold_bias[g * 64 + i], zz[i]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float w16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w16[i] = zz[q * 16 + i];
+          ptx::tmem_st16(t_acc + g * 64 + q * 16, w16);
+        }
+      }
+    }
 
     // ---- LayerNorm statistics of the four gates ------------------------------------------
     float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
@@ -604,11 +637,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
     }
     const bool clamp = (is_v ? a.clampV : a.clampE) != 0;
     if (is_v) {
-      if (clamp) k1_epilogue<HP, 0, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
-      else k1_epilogue<HP, 0, false>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+      if (clamp) k1_epilogue<HP, 0, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s, a.vdeg);
+      else k1_epilogue<HP, 0, false>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s, a.vdeg);
     } else {
-      if (clamp) k1_epilogue<HP, 1, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
-      else k1_epilogue<HP, 1, false>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s);
+      if (clamp) k1_epilogue<HP, 1, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s, a.vdeg);
+      else k1_epilogue<HP, 1, false>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s, a.vdeg);
     }
   } else {
     ptx::setmaxnreg_dec<104>();   // 128 x (168 - 104) = 8192 registers back to the CTA pool ...
@@ -658,13 +691,14 @@ __device__ __forceinline__ uint32_t stage_off(int r, int chunk) {
 }
 
 // ---- one warpgroup: epilogues of the layer chain of its tiles ------------------------------
-// ROLE 0 = V rows (V_msg_E, message stored), 1 = E rows (E_msg_V, scatter-add), 2 = E rows vote
+// ROLE 0 = V rows (V_msg_E, message stored), 1 = E rows (E_msg_V, scatter-add), 2 = E rows vote,
+// 3 = E rows with the output layer folded into the vertex cell (three layers, scatter-add of a3)
 template <int HP, int ROLE>
 __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64_t* acc_full, uint64_t* act_ready,
                                          uint64_t* slot_free, uint32_t tmem, int t0, int ntiles, int warp, int lane,
                                          uint32_t bias_s) {
   using L = K2Smem<HP>;
-  constexpr int NL = (ROLE == 2) ? 3 : 4;
+  constexpr int NL = (ROLE >= 2) ? 3 : 4;
   const int e = warp >> 2, q4 = warp & 3;
   const int r = q4 * 32 + lane;
   const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 64;
@@ -676,6 +710,12 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
     const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
     const int slot = n % L::NSLOT;
     const uint32_t b_s = slots_s + slot * L::SLOT_BYTES;
+    // endpoints of this warp's 32 rows, fetched a whole layer chain ahead of the scatter that uses them
+    int my_s = -1, my_d = -1;
+    if ((ROLE == 1 || ROLE == 3) && row0 + q4 * 32 + lane < n_rows) {
+      my_s = __ldg(a.src + row0 + q4 * 32 + lane);
+      my_d = __ldg(a.dst + row0 + q4 * 32 + lane);
+    }
     float v[64];
 #pragma unroll 1
     for (int l = 0; l < NL; ++l, ++step) {
@@ -683,9 +723,19 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
       tl_mark(tl, e, n, l);
       ptx::tcgen05_fence_after();
       ptx::tmem_ld64(t_acc, v);
-      const bool hidden = (ROLE == 2) || (l < 3);
+      const bool hidden = (ROLE >= 2) || (l < 3);
       const bool feeds_mma = l < NL - 1;
-      if (hidden) {
+      if (ROLE == 3 && !feeds_mma) {
+        // last hidden layer of the folded chain: bias + ReLU only, kept in fp32 for the scatter
+        const uint32_t bl = bias_s + l * 256;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 bb = ptx::lds128f(bl + q * 16);
+          const float2 x0 = ptx::relu2(__fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(bb.x, bb.y)));
+          const float2 x1 = ptx::relu2(__fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(bb.z, bb.w)));
+          v[4 * q] = x0.x; v[4 * q + 1] = x0.y; v[4 * q + 2] = x1.x; v[4 * q + 3] = x1.y;
+        }
+      } else if (hidden) {
         const uint32_t nxt = b_s + r * 16;          // in place: this layer's MMA has finished reading the slot
         const uint32_t bl = bias_s + l * 256;       // broadcast LDS.128: four bias values per load
 #pragma unroll
@@ -727,9 +777,13 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
       // row with 16-byte accesses)
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
-        const float4 bb = ptx::lds128f(bias_s + 3 * 256 + q * 16);
-        ptx::sts128f(b_s + stage_off(r, q),
-                     make_float4(v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w));
+        if (ROLE == 3) {
+          ptx::sts128f(b_s + stage_off(r, q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        } else {
+          const float4 bb = ptx::lds128f(bias_s + 3 * 256 + q * 16);
+          ptx::sts128f(b_s + stage_off(r, q),
+                       make_float4(v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w));
+        }
       }
       __syncwarp();
       const int64_t g0 = row0 + q4 * 32;
@@ -746,11 +800,6 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
       } else {
         // dst side: one vector reduction per row; src side accumulated over runs of equal src
         // (rows of a complete graph are sorted by src, instance_loader.py:60)
-        int my_s = -1, my_d = -1;
-        if (g0 + lane < n_rows) {
-          my_s = __ldg(a.src + g0 + lane);
-          my_d = __ldg(a.dst + g0 + lane);
-        }
         int cur_s = -1;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
@@ -758,7 +807,7 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
           const int rr = 2 * i + hw;
           const int s = __shfl_sync(0xffffffffu, my_s, rr);
           const int d = __shfl_sync(0xffffffffu, my_d, rr);
-          if (s >= 0) {
+          if (s >= 0 && !(a.fold & 2)) {
             const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
             ptx::red_add_v4(a.xV + static_cast<int64_t>(d) * D + 4 * c16, m);
             if (s != cur_s) {
@@ -882,10 +931,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   if (warp < 4 * K2_CHAINS) {
     if (a.vote_mode) k2_chain<HP, 2>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
     else if (is_v) k2_chain<HP, 0>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
+    else if (a.fold & 1) k2_chain<HP, 3>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
     else k2_chain<HP, 1>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
   } else if (warp == 12) {
     if (ntiles > 0)
-      k2_mma<HP>(wsm, slots, bar_w, slot_full, acc_full, act_ready, tmem, ntiles, a.vote_mode ? 3 : 4, a.timeline);
+      k2_mma<HP>(wsm, slots, bar_w, slot_full, acc_full, act_ready, tmem, ntiles,
+                 (a.vote_mode || ((a.fold & 1) && !is_v)) ? 3 : 4, a.timeline);
   } else if (warp == 13) {
     if (lane == 0) {
       for (int n = 0; n < ntiles; ++n) {
@@ -900,6 +951,15 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   ptx::tcgen05_fence_before();
   __syncthreads();
   if (warp == 12) ptx::tmem_dealloc(tmem, 256);
+}
+
+// deg[v] = number of edge rows incident to vertex v (K1Args::vdeg); `deg` must be zeroed first
+__global__ void __launch_bounds__(256) tc_degree_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                                        int64_t n_edges, float* __restrict__ deg) {
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  atomicAdd(deg + src[e], 1.0f);
+  atomicAdd(deg + dst[e], 1.0f);
 }
 
 // ====================================================================================

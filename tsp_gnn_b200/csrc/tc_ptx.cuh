@@ -188,6 +188,21 @@ __device__ __forceinline__ void tmem_ld16x3(uint32_t a0, uint32_t a1, uint32_t a
   }
 }
 
+// one 16-column load
+__device__ __forceinline__ void tmem_ld16(uint32_t a0, float (&v0)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(a0)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v0[i] = __uint_as_float(r[i]);
+}
+
 // two 16-column loads in flight, one wait
 __device__ __forceinline__ void tmem_ld16x2(uint32_t a0, uint32_t a1, float (&v0)[16], float (&v1)[16]) {
   uint32_t r[32];

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -132,6 +133,10 @@ struct tspgnn_ctx {
   float h_vinit[D];
   // tensor-core weight images
   uint8_t* d_wlstm[2] = {nullptr, nullptr};   // [0] V, [1] E
+  uint8_t* d_wlstm_vfold = nullptr;           // V cell with E_msg_V's output layer merged in: [W4.Kx ; Kh]
+  float h_vfold_bias[4 * D];                  // (b4 . Kx), centred per gate
+  float* d_deg = nullptr;                     // [sumV_pad] incident edges per vertex (folded path)
+  bool fold = true;                           // tensor-core modes: inference timesteps use the folded output layer
   uint8_t* d_wmlp[3] = {nullptr, nullptr, nullptr};   // V_msg_E, E_msg_V, E_vote
   // plan
   int B = 0;
@@ -181,6 +186,7 @@ static int upload_constants(tspgnn_ctx* h, cudaStream_t s) {
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_vote_tail, &h->h_vote_tail, sizeof(VoteTail), 0, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_einit, &h->h_einit, sizeof(EInit), 0, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyToSymbolAsync(c_vinit, h->h_vinit, sizeof(h->h_vinit), 0, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyToSymbolAsync(c_vfold_bias, h->h_vfold_bias, sizeof(h->h_vfold_bias), 0, cudaMemcpyHostToDevice, s));
   // pageable host memory: the copy may be staged asynchronously; make it safe to reuse
   CUDA_TRY(cudaStreamSynchronize(s));
   g_const_owner = h;
@@ -256,7 +262,7 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
     for (void* p : wp)
       if (p) cudaFree(p);
   }
-  void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote};
+  void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg};
   for (void* p : tp)
     if (p) cudaFree(p);
   if (g_const_owner == h) g_const_owner = nullptr;
@@ -344,6 +350,43 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
           make_b_image(kc.data(), 4 * D, kb * 64, 0, 256, p, img.data() + (p * 2 + kb) * 32768);
       if (!h->d_wlstm[c] && dev_alloc(&h->d_wlstm[c], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
       CUDA_TRY(cudaMemcpy(h->d_wlstm[c], img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
+    {
+      // V cell with the (linear) output layer of E_msg_V merged into the x half of its kernel:
+      //   x_V . Kx = (sum_e a3[e] . W4 + deg b4) . Kx = (sum_e a3[e]) . (W4 . Kx) + deg (b4 . Kx)
+      const float* K = blob + o.cell_k[0];
+      const float* W4 = blob + o.msg_w[1][3];
+      const float* b4 = blob + o.msg_b[1][3];
+      std::vector<double> row(4 * D);
+      for (int k = 0; k <= 2 * D; ++k) {            // k == 2*D: the bias row
+        for (int n = 0; n < 4 * D; ++n) {
+          double acc = 0.0;
+          if (k < D) {
+            for (int j = 0; j < D; ++j) acc += static_cast<double>(W4[k * D + j]) * K[static_cast<int64_t>(j) * 4 * D + n];
+          } else if (k < 2 * D) {
+            acc = K[static_cast<int64_t>(k) * 4 * D + n];
+          } else {
+            for (int j = 0; j < D; ++j) acc += static_cast<double>(b4[j]) * K[static_cast<int64_t>(j) * 4 * D + n];
+          }
+          row[n] = acc;
+        }
+        for (int g = 0; g < 4; ++g) {
+          double m = 0.0;
+          for (int n = 0; n < D; ++n) m += row[g * D + n];
+          m /= D;
+          for (int n = 0; n < D; ++n) {
+            const float v = static_cast<float>(row[g * D + n] - m);
+            if (k < 2 * D) kc[static_cast<size_t>(k) * 4 * D + g * D + n] = v;
+            else h->h_vfold_bias[g * D + n] = v;
+          }
+        }
+      }
+      img.assign(static_cast<size_t>(hp) * 2 * 32768, 0);
+      for (int p = 0; p < hp; ++p)
+        for (int kb = 0; kb < 2; ++kb)
+          make_b_image(kc.data(), 4 * D, kb * 64, 0, 256, p, img.data() + (p * 2 + kb) * 32768);
+      if (!h->d_wlstm_vfold && dev_alloc(&h->d_wlstm_vfold, static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
+      CUDA_TRY(cudaMemcpy(h->d_wlstm_vfold, img.data(), img.size(), cudaMemcpyHostToDevice));
     }
     for (int m = 0; m < 3; ++m) {
       img.assign(static_cast<size_t>(4) * hp * 8192, 0);
@@ -446,7 +489,8 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
     if (h->hp == 0) {
       if (dev_alloc(&h->Vc, nV_pad * D)) return TSPGNN_E_CUDA;
     } else {
-      if (dev_alloc(&h->stateV, nV_pad / TILE_ROWS * tile_bytes(h->hp))) return TSPGNN_E_CUDA;
+      if (dev_alloc(&h->stateV, nV_pad / TILE_ROWS * tile_bytes(h->hp)) || dev_alloc(&h->d_deg, nV_pad))
+        return TSPGNN_E_CUDA;
     }
     h->cap_V = nV_pad;
   }
@@ -470,6 +514,12 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
   CUDA_TRY(cudaMemcpy(h->d_eoff, eoff.data(), (n_instances + 1) * 8, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(h->xV, 0, nV_pad * D * 4));
   CUDA_TRY(cudaMemset(h->mV, 0, nV_pad * D * 4));
+  if (h->hp > 0) {
+    CUDA_TRY(cudaMemset(h->d_deg, 0, nV_pad * 4));
+    tc_degree_kernel<<<static_cast<int>((nE + 255) / 256), 256>>>(h->d_src, h->d_dst, nE, h->d_deg);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
   h->B = n_instances;
   h->nE = nE;
   h->nV = nV;
@@ -539,9 +589,12 @@ static void role_split(const tspgnn_ctx* h, int tilesE, int tilesV, double v_wei
 }
 
 template <int HP>
-static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, long long* timeline = nullptr) {
+static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, long long* timeline = nullptr) {
   K2Args a;
   a.timeline = timeline;
+  a.fold = (fold && !vote) ? 1 : 0;
+  static const bool no_scatter = getenv("TSPGNN_DEBUG_NOSCATTER") != nullptr;   // timing experiment only: results are wrong
+  if (no_scatter) a.fold |= 2;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = vote ? h->d_wmlp[2] : h->d_wmlp[1];
@@ -557,20 +610,21 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, long long* tim
   a.tilesV = vote ? 0 : h->tilesV;
   a.vote_mode = vote ? 1 : 0;
   int grid;
-  role_split(h, a.tilesE, a.tilesV, 0.8, grid, a.e_ctas);
+  role_split(h, a.tilesE, a.tilesV, a.fold ? 1.05 : 0.8, grid, a.e_ctas);
   CUDA_TRY(launch_pdl(tc_mlp_kernel<HP>, grid, K2_THREADS, K2Smem<HP>::DYN_BYTES, s, a));
   LAUNCH_CHECK(h);
   return 0;
 }
 
 template <int HP>
-static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, long long* timeline = nullptr) {
+static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, bool fold, long long* timeline = nullptr) {
   K1Args a;
   a.timeline = timeline;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = h->d_wlstm[1];
-  a.wV = h->d_wlstm[0];
+  a.wV = fold ? h->d_wlstm_vfold : h->d_wlstm[0];
+  a.vdeg = fold ? h->d_deg : nullptr;
   a.mV = h->mV;
   a.xV = h->xV;
   a.src = h->d_src;
@@ -582,7 +636,7 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, long long* timeline = nul
   a.clampV = h->clamp_cell[0];
   a.clampE = h->clamp_cell[1];
   int grid;
-  role_split(h, a.tilesE, a.tilesV, 1.35, grid, a.e_ctas);
+  role_split(h, a.tilesE, a.tilesV, fold ? 1.42 : 1.35, grid, a.e_ctas);
   CUDA_TRY(launch_pdl(tc_lnlstm_kernel<HP>, grid, TC_THREADS, K1Smem<HP>::DYN_BYTES, s, a));
   LAUNCH_CHECK(h);
   return 0;
@@ -603,7 +657,7 @@ static int simt_mlp(tspgnn_ctx* h, cudaStream_t s, const float* x, int64_t rows,
 
 // First half of while_body (graphnn.py:152-161): both message MLPs and the EV^T product; leaves
 // mV (vertex messages) and xV (summed edge messages) for the cells.
-static int step_messages(tspgnn_ctx* h, cudaStream_t s) {
+static int step_messages(tspgnn_ctx* h, cudaStream_t s, bool fold) {
   if (h->hp == 0) {
     // graphnn.py:142-173, both variables read the time-t states
     if (simt_mlp(h, s, h->Eh, h->nE, 1, h->mE)) return TSPGNN_E_CUDA;
@@ -612,11 +666,11 @@ static int step_messages(tspgnn_ctx* h, cudaStream_t s) {
     LAUNCH_CHECK(h);
     return 0;
   }
-  return (h->hp == 2) ? tc_launch_k2<2>(h, s, false) : tc_launch_k2<1>(h, s, false);
+  return (h->hp == 2) ? tc_launch_k2<2>(h, s, false, fold) : tc_launch_k2<1>(h, s, false, fold);
 }
 
 // Second half (graphnn.py:155-170): EV product (gather) + both LayerNorm-LSTM cells, in place.
-static int step_cells(tspgnn_ctx* h, cudaStream_t s) {
+static int step_cells(tspgnn_ctx* h, cudaStream_t s, bool fold) {
   if (h->hp == 0) {
     const int smem = (2 * D * 4 * D + 2 * D * XS_LD) * 4;
     const int gv = std::max(1, std::min(h->num_sms, grid_for(h->nV, SIMT_THREADS)));
@@ -629,12 +683,12 @@ static int step_cells(tspgnn_ctx* h, cudaStream_t s) {
     LAUNCH_CHECK(h);
     return 0;
   }
-  return (h->hp == 2) ? tc_launch_k1<2>(h, s) : tc_launch_k1<1>(h, s);
+  return (h->hp == 2) ? tc_launch_k1<2>(h, s, fold) : tc_launch_k1<1>(h, s, fold);
 }
 
 static int one_step(tspgnn_ctx* h, cudaStream_t s) {
-  if (step_messages(h, s)) return TSPGNN_E_CUDA;
-  return step_cells(h, s);
+  if (step_messages(h, s, h->fold)) return TSPGNN_E_CUDA;
+  return step_cells(h, s, h->fold);
 }
 
 extern "C" int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const float* dC, void* stream) {
@@ -722,9 +776,9 @@ extern "C" int tspgnn_readout(tspgnn_handle h, float* d_logits, float* d_predict
   if (h->hp == 0) {
     if (simt_mlp(h, s, h->Eh, h->nE, 2, h->vote)) return TSPGNN_E_CUDA;
   } else if (h->hp == 2) {
-    if (tc_launch_k2<2>(h, s, true)) return TSPGNN_E_CUDA;
+    if (tc_launch_k2<2>(h, s, true, false)) return TSPGNN_E_CUDA;
   } else {
-    if (tc_launch_k2<1>(h, s, true)) return TSPGNN_E_CUDA;
+    if (tc_launch_k2<1>(h, s, true, false)) return TSPGNN_E_CUDA;
   }
   readout_kernel<<<grid_for(static_cast<int64_t>(h->B) * 32, 128), 128, 0, s>>>(h->vote, h->d_eoff, h->B, d_logits,
                                                                                 d_predictions);
@@ -824,17 +878,17 @@ extern "C" int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* 
   for (int i = 0; i < iters; ++i) {
     // keep the producer/consumer pairing of xV intact: the kernel that is not timed runs untimed
     if (which == 0) {
-      int rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false) : tc_launch_k2<1>(h, s, false);
+      int rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold) : tc_launch_k2<1>(h, s, false, h->fold);
       if (rc) return rc;
     }
     CUDA_TRY(cudaEventRecord(e0, s));
     int rc;
-    if (which == 0) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s) : tc_launch_k1<1>(h, s);
-    else rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false) : tc_launch_k2<1>(h, s, false);
+    if (which == 0) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold) : tc_launch_k1<1>(h, s, h->fold);
+    else rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold) : tc_launch_k2<1>(h, s, false, h->fold);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(e1, s));
     if (which == 1) {
-      rc = (h->hp == 2) ? tc_launch_k1<2>(h, s) : tc_launch_k1<1>(h, s);
+      rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold) : tc_launch_k1<1>(h, s, h->fold);
       if (rc) return rc;
     }
     CUDA_TRY(cudaEventSynchronize(e1));
@@ -864,11 +918,11 @@ extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_
   CUDA_TRY(cudaMemsetAsync(d, 0, need * 8, s));
   int rc;
   if (which == 0) {
-    rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false) : tc_launch_k2<1>(h, s, false);
-    if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, d) : tc_launch_k1<1>(h, s, d);
+    rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold) : tc_launch_k2<1>(h, s, false, h->fold);
+    if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold, d) : tc_launch_k1<1>(h, s, h->fold, d);
   } else {
-    rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, d) : tc_launch_k2<1>(h, s, false, d);
-    if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s) : tc_launch_k1<1>(h, s);
+    rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold, d) : tc_launch_k2<1>(h, s, false, h->fold, d);
+    if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold) : tc_launch_k1<1>(h, s, h->fold);
   }
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(out_host, d, need * 8, cudaMemcpyDeviceToHost, s);

@@ -1,8 +1,9 @@
-"""Instance -> rank partitioning for data-parallel inference.
+"""Instance -> rank partitioning for data-parallel inference and training.
 
 EV is block-diagonal per instance (instance_loader.py:56-66) and the parameters are shared,
 so instances are independent units: each rank plans and runs its own sub-batch and the only
-exchange is one all-reduce of the zero-padded [B] logits vector.
+exchanges are one all-reduce of the zero-padded [B] logits vector per forward pass and one
+all-reduce of the flat gradient blob (115,529 floats) per training step.
 """
 import numpy as np
 
@@ -64,3 +65,28 @@ def all_reduce_logits(local_logits, idx, batch_size, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(full, op=dist.ReduceOp.SUM)
     return full
+
+
+def all_reduce_gradients(grads, loss=None):
+    """One all-reduce(sum), in place, of the flat gradient blob (and optionally the loss scalar)
+    over the default process group.  Each rank computed its blob with the GLOBAL batch size as
+    the divisor of the loss mean (tspgnn_backward's ``global_batch``), so the sum is the gradient
+    of model.py:157's reduce_mean over the whole batch; the global-norm clip and Adam then run
+    identically on every rank (tspgnn_apply_gradients), keeping the replicas bit-equal."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+        if loss is not None:
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+    return grads, loss
+
+
+def train_step_sharded(engine, dW, dC, d_route_exists, time_steps, global_batch):
+    """Data-parallel training step of one rank: forward + reverse pass on this rank's instances,
+    gradient all-reduce, optimizer.  Returns (loss of the whole batch, global gradient norm)."""
+    engine.train_forward(dW, dC, time_steps)
+    loss, grads = engine.backward(d_route_exists, global_batch)
+    engine.stream().synchronize()
+    all_reduce_gradients(grads, loss)
+    gnorm = engine.apply_gradients(grads)
+    return float(loss.cpu()[0]), gnorm
