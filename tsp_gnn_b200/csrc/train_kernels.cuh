@@ -46,10 +46,28 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
   float* Wm = smem;              // [K][N]
   float* xs = smem + K * N;      // [64][RG_XLD]
   const int tid = threadIdx.x;
-  for (int i = tid; i < K * N; i += RG_THREADS) {
-    const int k = i / N, n = i % N;
-    const int wi = TRANS ? n : k, wj = TRANS ? k : n;
-    Wm[i] = (wi < a.w_rows && wj < a.w_cols) ? a.w[static_cast<int64_t>(wi) * a.ldw + wj] : 0.f;
+  // Weights: 16-byte loads along the rows of the stored matrix (every ldw / w_cols in use is a
+  // multiple of 4 and every matrix starts 16-byte aligned in the blob).
+  if (!TRANS) {
+#pragma unroll 4
+    for (int i4 = tid; i4 < K * N / 4; i4 += RG_THREADS) {
+      const int k = i4 / (N / 4), n = (i4 % (N / 4)) * 4;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < a.w_rows && n < a.w_cols) w = *reinterpret_cast<const float4*>(a.w + static_cast<int64_t>(k) * a.ldw + n);
+      *reinterpret_cast<float4*>(Wm + k * N + n) = w;
+    }
+  } else {
+    // consecutive threads take consecutive n: conflict-free transposed stores
+#pragma unroll 4
+    for (int i4 = tid; i4 < K * N / 4; i4 += RG_THREADS) {
+      const int n = i4 % N, k = (i4 / N) * 4;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < a.w_rows && k < a.w_cols) w = *reinterpret_cast<const float4*>(a.w + static_cast<int64_t>(n) * a.ldw + k);
+      Wm[(k + 0) * N + n] = w.x;
+      Wm[(k + 1) * N + n] = w.y;
+      Wm[(k + 2) * N + n] = w.z;
+      Wm[(k + 3) * N + n] = w.w;
+    }
   }
   const int64_t n_tiles = (a.n_rows + RG_THREADS - 1) / RG_THREADS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -64,9 +82,26 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
         __syncthreads();   // previous users of xs (and the weight load) are done
         const float* xp = a.x[kb];
         const int xld = a.xld[kb];
-        for (int i = tid; i < RG_THREADS * 64; i += RG_THREADS) {
-          const int r = i >> 6, k = i & 63;
-          xs[k * RG_XLD + r] = (row0 + r < a.n_rows) ? xp[(row0 + r) * xld + k] : 0.f;
+        // 256 rows x 16 float4, coalesced; two passes of eight loads in flight per thread
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          float4 xv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+            const int r = i4 >> 4, c4 = i4 & 15;
+            xv[q] = (row0 + r < a.n_rows) ? *reinterpret_cast<const float4*>(xp + (row0 + r) * xld + c4 * 4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+            const int r = i4 >> 4, c4 = i4 & 15;
+            xs[(c4 * 4 + 0) * RG_XLD + r] = xv[q].x;
+            xs[(c4 * 4 + 1) * RG_XLD + r] = xv[q].y;
+            xs[(c4 * 4 + 2) * RG_XLD + r] = xv[q].z;
+            xs[(c4 * 4 + 3) * RG_XLD + r] = xv[q].w;
+          }
         }
         __syncthreads();
         const float* Wk = Wm + (kb * 64) * N + nb * 64;
@@ -89,14 +124,39 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
       __syncthreads();
       float* yp = a.y[nb];
       const int yld = a.yld[nb];
-      for (int i = tid; i < RG_THREADS * 64; i += RG_THREADS) {
-        const int r = i >> 6, j = i & 63;
-        if (row0 + r < a.n_rows) {
-          float v = xs[j * RG_XLD + r];
-          if (EPI & EPI_MASK) v = (a.mask[(row0 + r) * a.mld + j] > 0.f) ? v : 0.f;
-          float* dst = yp + (row0 + r) * yld + j;
-          if (EPI & EPI_ACCUM) v += *dst;
-          *dst = v;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        float4 mv[8], ov[8];
+        if (EPI & (EPI_MASK | EPI_ACCUM)) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+            const int r = i4 >> 4, c4 = i4 & 15;
+            mv[q] = ov[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < a.n_rows) {
+              if (EPI & EPI_MASK) mv[q] = *reinterpret_cast<const float4*>(a.mask + (row0 + r) * a.mld + c4 * 4);
+              if (EPI & EPI_ACCUM) ov[q] = *reinterpret_cast<const float4*>(yp + (row0 + r) * yld + c4 * 4);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+          const int r = i4 >> 4, c4 = i4 & 15;
+          if (row0 + r < a.n_rows) {
+            float4 v = make_float4(xs[(c4 * 4 + 0) * RG_XLD + r], xs[(c4 * 4 + 1) * RG_XLD + r],
+                                   xs[(c4 * 4 + 2) * RG_XLD + r], xs[(c4 * 4 + 3) * RG_XLD + r]);
+            if (EPI & EPI_MASK) {
+              v.x = (mv[q].x > 0.f) ? v.x : 0.f;
+              v.y = (mv[q].y > 0.f) ? v.y : 0.f;
+              v.z = (mv[q].z > 0.f) ? v.z : 0.f;
+              v.w = (mv[q].w > 0.f) ? v.w : 0.f;
+            }
+            if (EPI & EPI_ACCUM) {
+              v.x += ov[q].x; v.y += ov[q].y; v.z += ov[q].z; v.w += ov[q].w;
+            }
+            *reinterpret_cast<float4*>(yp + (row0 + r) * yld + c4 * 4) = v;
+          }
         }
       }
     }
