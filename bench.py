@@ -277,11 +277,30 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e = {"value": world * T_STEPS * args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(hW.nbytes + hC.nbytes + hsrc.nbytes + hdst.nbytes + nv.size * 4 + ne.size * 4
-                                     + 2 * nE * 4 + (nV + 1) * 4),
+           "h2d_bytes_per_step": int(hW.nbytes + hC.nbytes + hsrc.nbytes + hdst.nbytes + (BATCH + 1) * 8
+                                     + ((2 * nE * 4 + (nV + 1) * 4) if args.mode == "simt" else 0)),
            "d2h_bytes_per_step": int(2 * BATCH * 4), "ms_per_step": 1e3 * e2e_s / args.steps,
            "includes": "tspgnn_plan (incidence upload) + E_init + 32 timesteps + vote read-out + D2H"}
     assert np.all(np.isfinite(out))
+
+    # ---------------- training step (secondary) ---------------------------------
+    train = None
+    if args.train_steps > 0:
+        yf = np.asarray(y, dtype=np.float32)
+        eng.set_hyper()                                  # model.py:13-15 defaults
+        eng.plan(nv, ne, hsrc, hdst)
+        eng.train_step_host(hW, hC, yf, T_STEPS)         # warm-up (allocates snapshots / scratch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.train_steps):
+            tr_loss, _, _ = eng.train_step_host(hW, hC, yf, T_STEPS)
+        barrier()
+        tr_s = (time.perf_counter() - t0) / args.train_steps
+        train = {"ms_per_step": 1e3 * tr_s, "instances_per_s": world * BATCH / tr_s, "loss": tr_loss,
+                 "what": "tspgnn_train_step_host: H2D, training forward (32 timesteps, snapshots), reverse pass, "
+                         "L2 + clip + Adam, operand refresh, D2H (model.py:157-167); per-GPU batch, no gradient "
+                         "all-reduce in this leg"}
+        eng.set_params(params)                           # the legs below use the seeded variables again
 
     # ---------------- CPU baseline beside it (rank 0, N=1) ---------------------------------
     cpu = None
@@ -302,7 +321,8 @@ def run_ours(args):
                            "timesteps_per_step": T_STEPS, "l2": "flushed between steps (256 MiB fill); within a "
                            "step the 53.7 MB recurrent state is re-used across the 32 timesteps",
                            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "train_step": train}
         print(json.dumps(line))
     eng.close()
     if world > 1:
@@ -317,6 +337,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=3, help="training steps timed for the secondary train_step block (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
