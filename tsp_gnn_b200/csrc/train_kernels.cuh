@@ -14,8 +14,8 @@
 
 namespace tspgnn {
 
-constexpr int RG_THREADS = 256;            // rows per tile of rowgemm (thread = row)
-constexpr int RG_XLD = RG_THREADS + 1;     // transposed staging [k][row]
+constexpr int RG_THREADS = 256;            // threads per CTA = rows per tile of rowgemm
+constexpr int RG_XLD = 65;                 // row-major staging [row][64], +1 breaks bank conflicts
 constexpr int RG_MAXB = 4;                 // up to 4 blocks of 64 columns on either side
 
 struct RowGemmArgs {
@@ -34,18 +34,24 @@ struct RowGemmArgs {
 
 constexpr int EPI_NONE = 0, EPI_RELU = 1, EPI_MASK = 2, EPI_ACCUM = 4;
 
-__host__ __device__ constexpr int rowgemm_smem_bytes(int K, int N) { return (K * N + 64 * RG_XLD) * 4; }
+__host__ __device__ constexpr int rowgemm_smem_bytes(int K, int N) { return (K * N + RG_THREADS * RG_XLD) * 4; }
 
 // Y[r, n] = epi( sum_k X[r, k] * Wm[k, n] + bias[n] ),  K = 64*KB, N = 64*NB.
 // TRANS = false: Wm[k, n] = Ws[k, n];  TRANS = true: Wm[k, n] = Ws[n, k]  (dX = dY . W^T).
 // EPI flags: RELU, MASK (zero where the forward activation was not positive), ACCUM (Y += ...).
+// A CTA owns 256-row tiles; per (tile, 64-column block) thread (rg = tid / 8, cg = tid % 8) accumulates
+// the 8 x 8 micro-tile rows rg*8 .. +7 x columns {cg*4 .. +3, 32 + cg*4 .. +3}: per k-step eight
+// LDS.32 of x (four distinct rows per warp, broadcast) and two conflict-free LDS.128 of W feed 64 FMAs,
+// which balances the shared-memory pipe against the FMA pipe (a one-row-per-thread form needs 16
+// LDS.128 per 64 FMAs and is bound by shared-memory bandwidth at a quarter of the FMA rate).
 template <int KB, int NB, bool TRANS, int EPI>
 __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a) {
   extern __shared__ float smem[];
   constexpr int K = 64 * KB, N = 64 * NB;
   float* Wm = smem;              // [K][N]
-  float* xs = smem + K * N;      // [64][RG_XLD]
+  float* xs = smem + K * N;      // [256][RG_XLD]: the X operand, then the output block
   const int tid = threadIdx.x;
+  const int rg = tid >> 3, cg = tid & 7;
   // Weights: 16-byte loads along the rows of the stored matrix (every ldw / w_cols in use is a
   // multiple of 4 and every matrix starts 16-byte aligned in the blob).
   if (!TRANS) {
@@ -74,9 +80,19 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
     const int64_t row0 = tile * RG_THREADS;
 #pragma unroll 1
     for (int nb = 0; nb < NB; ++nb) {
-      float acc[64];
+      float acc[8][8];
+      {
+        float b8[8];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) acc[j] = (a.bias != nullptr && nb * 64 + j < a.bias_n) ? a.bias[nb * 64 + j] : 0.f;
+        for (int j = 0; j < 8; ++j) {
+          const int col = nb * 64 + (j >> 2) * 32 + cg * 4 + (j & 3);
+          b8[j] = (a.bias != nullptr && col < a.bias_n) ? a.bias[col] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = b8[j];
+      }
 #pragma unroll 1
       for (int kb = 0; kb < KB; ++kb) {
         __syncthreads();   // previous users of xs (and the weight load) are done
@@ -97,30 +113,36 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
           for (int q = 0; q < 8; ++q) {
             const int i4 = tid + (pass * 8 + q) * RG_THREADS;
             const int r = i4 >> 4, c4 = i4 & 15;
-            xs[(c4 * 4 + 0) * RG_XLD + r] = xv[q].x;
-            xs[(c4 * 4 + 1) * RG_XLD + r] = xv[q].y;
-            xs[(c4 * 4 + 2) * RG_XLD + r] = xv[q].z;
-            xs[(c4 * 4 + 3) * RG_XLD + r] = xv[q].w;
+            float* d = xs + r * RG_XLD + c4 * 4;
+            d[0] = xv[q].x; d[1] = xv[q].y; d[2] = xv[q].z; d[3] = xv[q].w;
           }
         }
         __syncthreads();
-        const float* Wk = Wm + (kb * 64) * N + nb * 64;
-#pragma unroll 2
+        const float* Wk = Wm + (kb * 64) * N + nb * 64 + cg * 4;
+        const float* xr = xs + (rg * 8) * RG_XLD;
+#pragma unroll 4
         for (int k = 0; k < 64; ++k) {
-          const float xv = xs[k * RG_XLD + tid];
+          const float4 w0 = *reinterpret_cast<const float4*>(Wk + k * N);
+          const float4 w1 = *reinterpret_cast<const float4*>(Wk + k * N + 32);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int j4 = 0; j4 < 16; ++j4) {
-            const float4 w = *reinterpret_cast<const float4*>(Wk + k * N + j4 * 4);
-            acc[j4 * 4 + 0] = fmaf(xv, w.x, acc[j4 * 4 + 0]);
-            acc[j4 * 4 + 1] = fmaf(xv, w.y, acc[j4 * 4 + 1]);
-            acc[j4 * 4 + 2] = fmaf(xv, w.z, acc[j4 * 4 + 2]);
-            acc[j4 * 4 + 3] = fmaf(xv, w.w, acc[j4 * 4 + 3]);
+          for (int i = 0; i < 8; ++i) {
+            const float xv = xr[i * RG_XLD + k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
           }
         }
       }
       __syncthreads();   // everyone is done reading xs as the X operand
 #pragma unroll
-      for (int j = 0; j < 64; ++j) xs[j * RG_XLD + tid] = (EPI & EPI_RELU) ? fmaxf(acc[j], 0.f) : acc[j];
+      for (int i = 0; i < 8; ++i) {
+        float* d = xs + (rg * 8 + i) * RG_XLD + cg * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = (EPI & EPI_RELU) ? fmaxf(acc[i][j], 0.f) : acc[i][j];
+          d[(j >> 2) * 32 + (j & 3)] = v;
+        }
+      }
       __syncthreads();
       float* yp = a.y[nb];
       const int yld = a.yld[nb];
@@ -144,8 +166,8 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
           const int i4 = tid + (pass * 8 + q) * RG_THREADS;
           const int r = i4 >> 4, c4 = i4 & 15;
           if (row0 + r < a.n_rows) {
-            float4 v = make_float4(xs[(c4 * 4 + 0) * RG_XLD + r], xs[(c4 * 4 + 1) * RG_XLD + r],
-                                   xs[(c4 * 4 + 2) * RG_XLD + r], xs[(c4 * 4 + 3) * RG_XLD + r]);
+            const float* sp = xs + r * RG_XLD + c4 * 4;
+            float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
             if (EPI & EPI_MASK) {
               v.x = (mv[q].x > 0.f) ? v.x : 0.f;
               v.y = (mv[q].y > 0.f) ? v.y : 0.f;
@@ -166,7 +188,10 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
 // ------------------------------------------------------------------------------------
 // dW[kb*64 + k, nb*64 + n] += sum_r X[r, kb*64 + k] * dY[r, nb*64 + n]      (blockIdx.y = kb, blockIdx.z = nb)
 // db[nb*64 + n]            += sum_r dY[r, nb*64 + n]                          (only the kb == 0 CTAs)
-// 256 threads, each a 4x4 block of the 64x64 tile; rows are streamed 32 at a time through shared memory.
+// 256 threads = 4 row groups x 64 threads; a group takes every fourth row of the 64-row chunks
+// streamed through shared memory, and each of its threads an 8 x 8 block of the 64 x 64 tile
+// (k = ty*8 .. +7, n = {tx*4 .. +3, 32 + tx*4 .. +3}): four conflict-free LDS.128 feed 64 FMAs.
+// The four partial tiles are summed in shared memory, then one fp32 atomic per element goes out.
 // ------------------------------------------------------------------------------------
 struct XtdyArgs {
   const float* x[RG_MAXB];
@@ -179,71 +204,92 @@ struct XtdyArgs {
   int64_t n_rows;
 };
 
-constexpr int XT_ROWS = 32;
+constexpr int XT_ROWS = 64;
 
 __global__ void __launch_bounds__(256) xtdy_kernel(const XtdyArgs a) {
   __shared__ __align__(16) float Xs[XT_ROWS][64];
   __shared__ __align__(16) float Ys[XT_ROWS][64];
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
+  const int g = tid >> 6, t = tid & 63;
+  const int ty = t >> 3, tx = t & 7;
   const int kb = blockIdx.y, nb = blockIdx.z;
   const float* xp = a.x[kb];
   const int xld = a.xld[kb];
   const float* yp = a.dy + nb * 64;
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bool do_bias = (a.db != nullptr) && kb == 0 && ty == 0;
   const int64_t n_chunks = (a.n_rows + XT_ROWS - 1) / XT_ROWS;
   for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     const int64_t row0 = ch * XT_ROWS;
     __syncthreads();
-    // 32 rows x 16 float4 per matrix = 512 float4 each; two per thread and matrix
+    // 64 rows x 16 float4 per matrix: four per thread and matrix, all loads in flight before the stores
+    float4 xv[4], yv[4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < 4; ++q) {
       const int i = tid + q * 256;
       const int r = i >> 4, c4 = i & 15;
-      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv;
+      xv[q] = yv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row0 + r < a.n_rows) {
-        xv = *reinterpret_cast<const float4*>(xp + (row0 + r) * xld + c4 * 4);
-        yv = *reinterpret_cast<const float4*>(yp + (row0 + r) * a.dyld + c4 * 4);
+        xv[q] = *reinterpret_cast<const float4*>(xp + (row0 + r) * xld + c4 * 4);
+        yv[q] = *reinterpret_cast<const float4*>(yp + (row0 + r) * a.dyld + c4 * 4);
       }
-      *reinterpret_cast<float4*>(&Xs[r][c4 * 4]) = xv;
-      *reinterpret_cast<float4*>(&Ys[r][c4 * 4]) = yv;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = tid + q * 256;
+      const int r = i >> 4, c4 = i & 15;
+      *reinterpret_cast<float4*>(&Xs[r][c4 * 4]) = xv[q];
+      *reinterpret_cast<float4*>(&Ys[r][c4 * 4]) = yv[q];
     }
     __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < XT_ROWS; ++r) {
-      const float4 xv = *reinterpret_cast<const float4*>(&Xs[r][ty * 4]);
-      const float4 yv = *reinterpret_cast<const float4*>(&Ys[r][tx * 4]);
-      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-      const float ya[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll 4
+    for (int rr = 0; rr < XT_ROWS / 4; ++rr) {
+      const int r = rr * 4 + g;
+      const float4 x0 = *reinterpret_cast<const float4*>(&Xs[r][ty * 8]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&Xs[r][ty * 8 + 4]);
+      const float4 y0 = *reinterpret_cast<const float4*>(&Ys[r][tx * 4]);
+      const float4 y1 = *reinterpret_cast<const float4*>(&Ys[r][32 + tx * 4]);
+      const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xa[i], ya[j], acc[i][j]);
       if (do_bias) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bs[j] += ya[j];
+        for (int j = 0; j < 8; ++j) bs[j] += ya[j];
       }
     }
   }
+  // sum the four row groups in shared memory (re-using the staging buffers), then one atomic per element
+  __syncthreads();
+  float* red = &Xs[0][0];     // [64][64]
+  float* redb = &Ys[0][0];    // [64]
+  for (int i = tid; i < 64 * 64; i += 256) red[i] = 0.f;
+  if (tid < 64) redb[tid] = 0.f;
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int wi = kb * 64 + ty * 4 + i, wj = nb * 64 + tx * 4 + j;
-      if (wi < a.w_rows && wj < a.w_cols) atomicAdd(a.dw + static_cast<int64_t>(wi) * a.ldw + wj, acc[i][j]);
-    }
+    for (int j = 0; j < 8; ++j)
+      atomicAdd(red + (ty * 8 + i) * 64 + (j >> 2) * 32 + tx * 4 + (j & 3), acc[i][j]);
   if (do_bias) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int wj = nb * 64 + tx * 4 + j;
-      if (wj < a.w_cols) atomicAdd(a.db + wj, bs[j]);
-    }
+    for (int j = 0; j < 8; ++j) atomicAdd(redb + (j >> 2) * 32 + tx * 4 + (j & 3), bs[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 64 * 64; i += 256) {
+    const int wi = kb * 64 + (i >> 6), wj = nb * 64 + (i & 63);
+    if (wi < a.w_rows && wj < a.w_cols) atomicAdd(a.dw + static_cast<int64_t>(wi) * a.ldw + wj, red[i]);
+  }
+  if (a.db != nullptr && kb == 0 && tid < 64) {
+    const int wj = nb * 64 + tid;
+    if (wj < a.w_cols) atomicAdd(a.db + wj, redb[tid]);
   }
 }
 
