@@ -240,6 +240,15 @@ def test_world_size_2_gloo_gradient_allreduce(tmp_path):
     assert "GLOO_GRAD_OK 2" in res.stdout
 
 
+def test_binary_search_bounds_follow_the_reference():
+    """experiments/binary_search.py:23-34 on a 4-city instance (values worked out by hand)."""
+    from tsp_gnn_b200 import experiments
+    Mw = np.array([[0, 1, 2, 3], [1, 0, 4, 5], [2, 4, 0, 6], [3, 5, 6, 0]], dtype=float)
+    lo, hi = experiments.cost_bounds(Mw)
+    # triu/tril each hold 10 zeros and {1,2,3,4,5,6}: the 4 lightest entries are zeros, the 4 heaviest 3+4+5+6
+    assert lo == 0.0 and hi == 18.0 / 4
+
+
 def test_library_exports_every_declared_symbol():
     from tsp_gnn_b200 import _lib
     header = open(os.path.join(ROOT, "include", "tspgnn.h")).read()

@@ -32,12 +32,15 @@ with torch.cuda.stream(s):
 s.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 losses = []
+first = None
 for step in range(3):
     ev0.record(s)
     loss, gnorm = sharding.train_step_sharded(eng, dW, dC, dy, T, len(sizes))
     ev1.record(s)
     s.synchronize()
     losses.append(loss)
+    if step == 0:
+        first = eng.get_params()
 mine = torch.from_numpy(eng.get_params()).to(dev)
 others = [torch.empty_like(mine) for _ in range(world)]
 dist.all_gather(others, mine)
@@ -47,14 +50,15 @@ if rank == 0:
     ref.set_params(params)
     ref.set_hyper(learning_rate=1e-3)
     ref.plan(nv, ne, EV.src, EV.dst)
-    ref_losses = [ref.train_step_host(W, C, y, T)[0] for _ in range(3)]
+    ref_losses = [ref.train_step_host(W, C, y, T)[0]]
     # the first step sees identical variables: the reduced gradient equals the whole-batch gradient up to fp32
-    # summation order; later steps inherit Adam's sensitivity where |g| ~ eps
+    # summation order; later steps inherit Adam's sensitivity where |g| ~ eps (sign-like updates)
+    d = np.abs(ref.get_params() - first)
+    ref_losses += [ref.train_step_host(W, C, y, T)[0] for _ in range(2)]
     print("losses sharded", losses, "single", ref_losses)
-    assert abs(losses[0] - ref_losses[0]) < 1e-5
-    d = np.abs(ref.get_params() - mine.cpu().numpy())
-    print("max |dvar| after 3 steps %.3e (lr 1e-3), 99th pct %.3e" % (d.max(), np.quantile(d, 0.99)))
-    assert np.quantile(d, 0.9) < 1e-4
+    assert abs(losses[0] - ref_losses[0]) < 1e-5 and abs(losses[1] - ref_losses[1]) < 1e-5
+    print("|dvar| after the first step: max %.3e, 90th pct %.3e (lr 1e-3)" % (d.max(), np.quantile(d, 0.9)))
+    assert np.quantile(d, 0.9) < 5e-5 and d.max() < 2.5e-3
     print("DDP_TRAIN_OK world=%d last step %.2f ms" % (world, ev0.elapsed_time(ev1)))
     ref.close()
 eng.close()

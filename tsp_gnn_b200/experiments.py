@@ -1,0 +1,45 @@
+"""Inference loops of the reference's experiment scripts on top of ``Session``.
+
+``get_cost`` mirrors experiments/binary_search.py:13-77: a binary search on the target cost C that
+repeatedly evaluates ``predictions`` on the SAME graph.  ``Session.run`` recognises the unchanged
+incidence and skips ``tspgnn_plan``; every probe then costs E_init + the timestep loop + read-out.
+"""
+import numpy as np
+
+from .instances import create_batch
+
+
+def cost_bounds(Mw):
+    """binary_search.py:23-34: sum of the n lightest / heaviest entries of triu and tril (zeros of the
+    other triangle included, as in the reference), normalised by n."""
+    n = Mw.shape[0]
+    wmin = np.minimum(np.sum(np.sort(np.triu(Mw).flatten())[:n]), np.sum(np.sort(np.tril(Mw).flatten())[:n]))
+    wmax = np.maximum(np.sum(np.sort(np.triu(Mw).flatten())[-n:]), np.sum(np.sort(np.tril(Mw).flatten())[-n:]))
+    return wmin / n, wmax / n
+
+
+def get_cost(sess, model, instance, time_steps, threshold=0.5, stopping_delta=0.01, max_iterations=64):
+    """Returns (wpred, pred, route_cost, iterations) like binary_search.py:13-77."""
+    Ma, Mw, route = instance
+    n = Ma.shape[0]
+    wmin, wmax = cost_bounds(Mw)
+    wpred = (wmin + wmax) / 2
+    route = list(route)
+    # binary_search.py:40 closes the tour correctly (route[1:] + route[:1]), unlike instance_loader.py:70
+    route_cost = sum(Mw[min(i, j), max(i, j)] for i, j in zip(route, route[1:] + route[:1])) / n
+    EV, W, _, route_exists, n_vertices, n_edges = create_batch([(Ma, Mw, route)], target_cost=wpred)
+    m = int(np.sum(n_edges))
+    C = np.ones((m, 1), dtype=np.float32)
+    feed = {model["EV"]: EV, model["W"]: W, model["C"]: None, model["time_steps"]: time_steps,
+            model["route_exists"]: route_exists, model["n_vertices"]: n_vertices, model["n_edges"]: n_edges}
+    iterations, pred = 0, None
+    while (wmin < wpred * (1 - stopping_delta) or wpred * (1 + stopping_delta) < wmax) and iterations < max_iterations:
+        feed[model["C"]] = C * wpred
+        pred = float(np.asarray(sess.run(model["predictions"], feed_dict=feed)).reshape(-1)[0])
+        if pred < threshold:
+            wmin = wpred
+        else:
+            wmax = wpred
+        wpred = (wmax + wmin) / 2
+        iterations += 1
+    return wpred, pred, route_cost, iterations

@@ -84,9 +84,14 @@ def all_reduce_gradients(grads, loss=None):
 def train_step_sharded(engine, dW, dC, d_route_exists, time_steps, global_batch):
     """Data-parallel training step of one rank: forward + reverse pass on this rank's instances,
     gradient all-reduce, optimizer.  Returns (loss of the whole batch, global gradient norm)."""
+    import torch
     engine.train_forward(dW, dC, time_steps)
     loss, grads = engine.backward(d_route_exists, global_batch)
-    engine.stream().synchronize()
-    all_reduce_gradients(grads, loss)
-    gnorm = engine.apply_gradients(grads)
-    return float(loss.cpu()[0]), gnorm
+    # The collective must be ordered on the engine's stream: torch's NCCL group synchronises its own
+    # stream with the CURRENT stream on both sides of the call, and the kernels that produce and
+    # consume the blob run on engine.stream(), not on torch's default stream.
+    with torch.cuda.stream(engine.stream()):
+        all_reduce_gradients(grads, loss)
+        loss_host = loss.cpu()
+    gnorm = engine.apply_gradients(grads)          # synchronises the stream
+    return float(loss_host[0]), gnorm
