@@ -246,6 +246,33 @@ def test_binary_search_cost_loop_runs_on_the_cached_plan():
         assert sess._engine.launch_count > 0
 
 
+def test_example_drivers_train_save_and_evaluate(tmp_path):
+    """examples/train.py + examples/test.py: the reference's train.py / test.py control flow (flags, run_batch,
+    log.dat, checkpoint directory naming) end to end on a tiny generated dataset."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "train.py"), "-epochs", "2", "-batchsize", "4",
+                        "-timesteps", "8", "-samples_train", "24", "-samples_test", "8", "-batches_train", "3",
+                        "-batches_test", "2", "--save"], cwd=str(tmp_path), env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Train Epoch 1 Average" in r.stdout and "Test Epoch 1 Average" in r.stdout
+    log = open(tmp_path / "training" / "dev=0.02" / "log.dat").read().strip().splitlines()
+    assert len(log) == 2 and all(len(line.split()) == 17 for line in log)          # train.py:253-276
+    ckpt = tmp_path / "training" / "dev=0.02" / "checkpoints" / "epoch=100"        # train.py:249
+    assert (ckpt / "model.npz").exists()
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "test.py"), "-time_steps", "8", "-checkpoint",
+                        str(ckpt)], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Test Epoch 0 Average" in r.stdout
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "test.py"), "-checkpoint", "nowhere"],
+                       cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "Path does not exist!" in r.stderr                # util.py:20
+
+
 def test_backward_requires_a_training_forward():
     from tsp_gnn_b200.engine import Engine
     from tsp_gnn_b200._lib import TspGnnError

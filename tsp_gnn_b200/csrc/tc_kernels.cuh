@@ -991,6 +991,57 @@ __global__ void __launch_bounds__(256) tc_pack_state_kernel(const float* __restr
   }
 }
 
+// E0 = E_init_MLP([W, C]) written straight into the edge tile images, c = 0 (model.py:33-43,
+// graphnn.py:134-139): same arithmetic as simt_edge_init_kernel, but thread = row of a tile, so the
+// 16-byte chunk stores of a warp are contiguous (512 B) instead of one 256-byte row per thread, and
+// the separate pack / zero passes disappear.  One CTA per tile.
+template <int HP>
+__global__ void __launch_bounds__(TILE_ROWS) tc_edge_init_kernel(const float* __restrict__ W, const float* __restrict__ C,
+                                                                 int64_t n_rows, uint8_t* __restrict__ state) {
+  const int r = threadIdx.x;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * TILE_ROWS + r;
+  uint8_t* tile = state + static_cast<int64_t>(blockIdx.x) * tile_bytes(HP);
+  const bool valid = row < n_rows;
+  const float in0 = valid ? W[row] : 0.f, in1 = valid ? C[row] : 0.f;
+  float a1[8], a2[16], a3[32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    a1[j] = fmaxf(fmaf(in1, c_einit.w1[1][j], fmaf(in0, c_einit.w1[0][j], c_einit.b1[j])), 0.f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float s = c_einit.b2[j];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = fmaf(a1[k], c_einit.w2[k][j], s);
+    a2[j] = fmaxf(s, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float s = c_einit.b3[j];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s = fmaf(a2[k], c_einit.w3[k][j], s);
+    a3[j] = fmaxf(s, 0.f);
+  }
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = ch * 8 + q;
+      float s = c_einit.b4[j];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) s = fmaf(a3[k], c_einit.w4[k][j], s);
+      o[q] = valid ? s : 0.f;            // padded rows are zero like tc_pack_state_kernel leaves them
+    }
+    uint4 hi, lo;
+    split8(o, hi, lo);
+    *reinterpret_cast<uint4*>(tile + ch * 2048 + r * 16) = hi;
+    if (HP == 2) *reinterpret_cast<uint4*>(tile + PLANE_BYTES + ch * 2048 + r * 16) = lo;
+  }
+  float4* cg = reinterpret_cast<float4*>(tile + HP * PLANE_BYTES) + r;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) cg[q * 128] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // zero the c tile of every state tile (graphnn.py:137)
 template <int HP>
 __global__ void __launch_bounds__(256) tc_zero_c_kernel(int64_t n_rows_pad, uint8_t* __restrict__ state) {

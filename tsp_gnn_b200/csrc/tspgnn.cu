@@ -714,30 +714,26 @@ extern "C" int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   if (upload_constants(h, s)) return TSPGNN_E_CUDA;
-  simt_edge_init_kernel<<<grid_for(h->nE, 256), 256, 0, s>>>(dW, dC, h->nE, h->Eh);
-  LAUNCH_CHECK(h);
   simt_vertex_init_kernel<<<grid_for(h->nV * D, 256), 256, 0, s>>>(h->nV, h->Vh);
   LAUNCH_CHECK(h);
   if (h->hp == 0) {
+    simt_edge_init_kernel<<<grid_for(h->nE, 256), 256, 0, s>>>(dW, dC, h->nE, h->Eh);
+    LAUNCH_CHECK(h);
     CUDA_TRY(cudaMemsetAsync(h->Ec, 0, h->nE_pad * D * 4, s));
     CUDA_TRY(cudaMemsetAsync(h->Vc, 0, h->nV_pad * D * 4, s));
   } else {
     CUDA_TRY(cudaMemsetAsync(h->xV, 0, h->nV_pad * D * 4, s));
     if (h->hp == 2) {
-      tc_pack_state_kernel<2><<<grid_for(h->nE_pad * 32, 256), 256, 0, s>>>(h->Eh, nullptr, h->nE, h->nE_pad, h->stateE);
+      tc_edge_init_kernel<2><<<h->tilesE, TILE_ROWS, 0, s>>>(dW, dC, h->nE, h->stateE);
       LAUNCH_CHECK(h);
       tc_pack_state_kernel<2><<<grid_for(h->nV_pad * 32, 256), 256, 0, s>>>(h->Vh, nullptr, h->nV, h->nV_pad, h->stateV);
-      LAUNCH_CHECK(h);
-      tc_zero_c_kernel<2><<<grid_for(h->nE_pad * 16, 256), 256, 0, s>>>(h->nE_pad, h->stateE);
       LAUNCH_CHECK(h);
       tc_zero_c_kernel<2><<<grid_for(h->nV_pad * 16, 256), 256, 0, s>>>(h->nV_pad, h->stateV);
       LAUNCH_CHECK(h);
     } else {
-      tc_pack_state_kernel<1><<<grid_for(h->nE_pad * 32, 256), 256, 0, s>>>(h->Eh, nullptr, h->nE, h->nE_pad, h->stateE);
+      tc_edge_init_kernel<1><<<h->tilesE, TILE_ROWS, 0, s>>>(dW, dC, h->nE, h->stateE);
       LAUNCH_CHECK(h);
       tc_pack_state_kernel<1><<<grid_for(h->nV_pad * 32, 256), 256, 0, s>>>(h->Vh, nullptr, h->nV, h->nV_pad, h->stateV);
-      LAUNCH_CHECK(h);
-      tc_zero_c_kernel<1><<<grid_for(h->nE_pad * 16, 256), 256, 0, s>>>(h->nE_pad, h->stateE);
       LAUNCH_CHECK(h);
       tc_zero_c_kernel<1><<<grid_for(h->nV_pad * 16, 256), 256, 0, s>>>(h->nV_pad, h->stateV);
       LAUNCH_CHECK(h);
