@@ -80,6 +80,23 @@ def test_gradients_match_oracle_small_ragged_batch(mode, T):
     check_grads(blob, ref["grads"], GRAD_RTOL[mode], label="%s T=%d" % (mode, T))
 
 
+def test_gradients_match_oracle_edge_sized_tiles():
+    """50 x n=40 = 39,000 edge rows: enough 256-row tiles to fill the 148 SMs, so the reverse pass takes its
+    edge-sized code path (256-row rowgemm tiles) for E and the vertex-sized one (64-row tiles) for V; fp32
+    forward, so the kernels are gated at 1e-4 of scale."""
+    from tsp_gnn_b200.engine import Engine
+    EV, W, C, y, nv, ne = inst.synth_batch([40] * 50, seed=17)
+    params = orc.init_params(64, seed=6, perturb_ln=True)
+    ref = og.forward_backward(params, EV.src, EV.dst, W, C, nv, ne, y, 2)
+    eng = Engine(64, "simt", 0)
+    eng.set_params(params)
+    eng.plan(nv, ne, EV.src, EV.dst)
+    loss, logits, blob = run_backward(eng, W, C, y, 2)
+    eng.close()
+    assert abs(loss - ref["loss"]) < 1e-5
+    check_grads(blob, ref["grads"], GRAD_RTOL["simt"], label="edge-sized tiles")
+
+
 def test_gradients_match_oracle_config1():
     """BASELINE config 1 (16 x n=20, 32 timesteps), reference initialisers."""
     from tsp_gnn_b200.engine import Engine

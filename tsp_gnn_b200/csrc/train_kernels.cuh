@@ -34,22 +34,27 @@ struct RowGemmArgs {
 
 constexpr int EPI_NONE = 0, EPI_RELU = 1, EPI_MASK = 2, EPI_ACCUM = 4;
 
-__host__ __device__ constexpr int rowgemm_smem_bytes(int K, int N) { return (K * N + RG_THREADS * RG_XLD) * 4; }
+__host__ __device__ constexpr int rowgemm_smem_bytes(int K, int N, int RPT) { return (K * N + 32 * RPT * RG_XLD) * 4; }
 
 // Y[r, n] = epi( sum_k X[r, k] * Wm[k, n] + bias[n] ),  K = 64*KB, N = 64*NB.
 // TRANS = false: Wm[k, n] = Ws[k, n];  TRANS = true: Wm[k, n] = Ws[n, k]  (dX = dY . W^T).
 // EPI flags: RELU, MASK (zero where the forward activation was not positive), ACCUM (Y += ...).
-// A CTA owns 256-row tiles; per (tile, 64-column block) thread (rg = tid / 8, cg = tid % 8) accumulates
-// the 8 x 8 micro-tile rows rg*8 .. +7 x columns {cg*4 .. +3, 32 + cg*4 .. +3}: per k-step eight
+// A CTA owns tiles of 32*RPT rows (RPT = 8: 256 rows for the edge-sized matrices; RPT = 2: 64 rows, so
+// that the vertex-sized ones still spread over 80 CTAs instead of 20); per (tile, 64-column block)
+// thread (rg = tid / 8, cg = tid % 8) accumulates the RPT x 8 micro-tile rows rg*RPT .. x columns
+// {cg*4 .. +3, 32 + cg*4 .. +3}.  With RPT = 8, per k-step eight
 // LDS.32 of x (four distinct rows per warp, broadcast) and two conflict-free LDS.128 of W feed 64 FMAs,
 // which balances the shared-memory pipe against the FMA pipe (a one-row-per-thread form needs 16
 // LDS.128 per 64 FMAs and is bound by shared-memory bandwidth at a quarter of the FMA rate).
-template <int KB, int NB, bool TRANS, int EPI>
+template <int KB, int NB, bool TRANS, int EPI, int RPT>
 __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a) {
   extern __shared__ float smem[];
   constexpr int K = 64 * KB, N = 64 * NB;
+  constexpr int TILE_R = 32 * RPT;                        // rows per tile
+  constexpr int PASSES = (RPT == 8) ? 2 : 1;              // staging passes
+  constexpr int PER = TILE_R * 16 / RG_THREADS / PASSES;  // float4 per thread and pass
   float* Wm = smem;              // [K][N]
-  float* xs = smem + K * N;      // [256][RG_XLD]: the X operand, then the output block
+  float* xs = smem + K * N;      // [TILE_R][RG_XLD]: the X operand, then the output block
   const int tid = threadIdx.x;
   const int rg = tid >> 3, cg = tid & 7;
   // Weights: 16-byte loads along the rows of the stored matrix (every ldw / w_cols in use is a
@@ -75,12 +80,12 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
       Wm[(k + 3) * N + n] = w.w;
     }
   }
-  const int64_t n_tiles = (a.n_rows + RG_THREADS - 1) / RG_THREADS;
+  const int64_t n_tiles = (a.n_rows + TILE_R - 1) / TILE_R;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * RG_THREADS;
+    const int64_t row0 = tile * TILE_R;
 #pragma unroll 1
     for (int nb = 0; nb < NB; ++nb) {
-      float acc[8][8];
+      float acc[RPT][8];
       {
         float b8[8];
 #pragma unroll
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
           b8[j] = (a.bias != nullptr && col < a.bias_n) ? a.bias[col] : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < RPT; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[i][j] = b8[j];
       }
@@ -98,20 +103,20 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
         __syncthreads();   // previous users of xs (and the weight load) are done
         const float* xp = a.x[kb];
         const int xld = a.xld[kb];
-        // 256 rows x 16 float4, coalesced; two passes of eight loads in flight per thread
+        // TILE_R rows x 16 float4, coalesced; PER loads in flight per thread and pass
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          float4 xv[8];
+        for (int pass = 0; pass < PASSES; ++pass) {
+          float4 xv[PER];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+          for (int q = 0; q < PER; ++q) {
+            const int i4 = tid + (pass * PER + q) * RG_THREADS;
             const int r = i4 >> 4, c4 = i4 & 15;
             xv[q] = (row0 + r < a.n_rows) ? *reinterpret_cast<const float4*>(xp + (row0 + r) * xld + c4 * 4)
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+          for (int q = 0; q < PER; ++q) {
+            const int i4 = tid + (pass * PER + q) * RG_THREADS;
             const int r = i4 >> 4, c4 = i4 & 15;
             float* d = xs + r * RG_XLD + c4 * 4;
             d[0] = xv[q].x; d[1] = xv[q].y; d[2] = xv[q].z; d[3] = xv[q].w;
@@ -119,14 +124,14 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
         }
         __syncthreads();
         const float* Wk = Wm + (kb * 64) * N + nb * 64 + cg * 4;
-        const float* xr = xs + (rg * 8) * RG_XLD;
+        const float* xr = xs + (rg * RPT) * RG_XLD;
 #pragma unroll 4
         for (int k = 0; k < 64; ++k) {
           const float4 w0 = *reinterpret_cast<const float4*>(Wk + k * N);
           const float4 w1 = *reinterpret_cast<const float4*>(Wk + k * N + 32);
           const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < RPT; ++i) {
             const float xv = xr[i * RG_XLD + k];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
       }
       __syncthreads();   // everyone is done reading xs as the X operand
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float* d = xs + (rg * 8 + i) * RG_XLD + cg * 4;
+      for (int i = 0; i < RPT; ++i) {
+        float* d = xs + (rg * RPT + i) * RG_XLD + cg * 4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float v = (EPI & EPI_RELU) ? fmaxf(acc[i][j], 0.f) : acc[i][j];
@@ -147,12 +152,12 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
       float* yp = a.y[nb];
       const int yld = a.yld[nb];
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        float4 mv[8], ov[8];
+      for (int pass = 0; pass < PASSES; ++pass) {
+        float4 mv[PER], ov[PER];
         if (EPI & (EPI_MASK | EPI_ACCUM)) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+          for (int q = 0; q < PER; ++q) {
+            const int i4 = tid + (pass * PER + q) * RG_THREADS;
             const int r = i4 >> 4, c4 = i4 & 15;
             mv[q] = ov[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row0 + r < a.n_rows) {
@@ -162,8 +167,8 @@ __global__ void __launch_bounds__(RG_THREADS) rowgemm_kernel(const RowGemmArgs a
           }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i4 = tid + (pass * 8 + q) * RG_THREADS;
+        for (int q = 0; q < PER; ++q) {
+          const int i4 = tid + (pass * PER + q) * RG_THREADS;
           const int r = i4 >> 4, c4 = i4 & 15;
           if (row0 + r < a.n_rows) {
             const float* sp = xs + r * RG_XLD + c4 * 4;
