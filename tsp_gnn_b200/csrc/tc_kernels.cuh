@@ -997,7 +997,15 @@ __global__ void __launch_bounds__(256) tc_pack_state_kernel(const float* __restr
 // the separate pack / zero passes disappear.  One CTA per tile.
 template <int HP>
 __global__ void __launch_bounds__(TILE_ROWS) tc_edge_init_kernel(const float* __restrict__ W, const float* __restrict__ C,
-                                                                 int64_t n_rows, uint8_t* __restrict__ state) {
+                                                                 const float* __restrict__ einit_blob, int64_t n_rows,
+                                                                 uint8_t* __restrict__ state) {
+  // The 2,824 parameters of E_init_MLP sit contiguously in the blob in EInit's member order; staged in
+  // shared memory they are read with warp-uniform (broadcast) LDS instead of 2,704 distinct
+  // constant-bank operands per thread, which thrash the constant cache.
+  __shared__ __align__(16) float wbuf[sizeof(EInit) / 4];
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(EInit) / 4); i += TILE_ROWS) wbuf[i] = einit_blob[i];
+  __syncthreads();
+  const EInit& P = *reinterpret_cast<const EInit*>(wbuf);
   const int r = threadIdx.x;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * TILE_ROWS + r;
   uint8_t* tile = state + static_cast<int64_t>(blockIdx.x) * tile_bytes(HP);
@@ -1005,33 +1013,33 @@ __global__ void __launch_bounds__(TILE_ROWS) tc_edge_init_kernel(const float* __
   const float in0 = valid ? W[row] : 0.f, in1 = valid ? C[row] : 0.f;
   float a1[8], a2[16], a3[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    a1[j] = fmaxf(fmaf(in1, c_einit.w1[1][j], fmaf(in0, c_einit.w1[0][j], c_einit.b1[j])), 0.f);
+  for (int j = 0; j < 8; ++j) a1[j] = fmaxf(fmaf(in1, P.w1[1][j], fmaf(in0, P.w1[0][j], P.b1[j])), 0.f);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float s = c_einit.b2[j];
+    float s = P.b2[j];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s = fmaf(a1[k], c_einit.w2[k][j], s);
+    for (int k = 0; k < 8; ++k) s = fmaf(a1[k], P.w2[k][j], s);
     a2[j] = fmaxf(s, 0.f);
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    float s = c_einit.b3[j];
+    float s = P.b3[j];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s = fmaf(a2[k], c_einit.w3[k][j], s);
+    for (int k = 0; k < 16; ++k) s = fmaf(a2[k], P.w3[k][j], s);
     a3[j] = fmaxf(s, 0.f);
   }
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
     float o[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int j = ch * 8 + q;
-      float s = c_einit.b4[j];
+    for (int q = 0; q < 8; ++q) o[q] = P.b4[ch * 8 + q];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) s = fmaf(a3[k], c_einit.w4[k][j], s);
-      o[q] = valid ? s : 0.f;            // padded rows are zero like tc_pack_state_kernel leaves them
+    for (int k = 0; k < 32; ++k) {       // k outer: the eight weights of a k are two LDS.128
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = fmaf(a3[k], P.w4[k][ch * 8 + q], o[q]);
     }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = valid ? o[q] : 0.f;   // padded rows are zero like tc_pack_state_kernel leaves them
     uint4 hi, lo;
     split8(o, hi, lo);
     *reinterpret_cast<uint4*>(tile + ch * 2048 + r * 16) = hi;

@@ -341,7 +341,7 @@ __device__ __forceinline__ void ln_bwd2(const float (&dy)[2], const float (&uh)[
   du[1] = r * (a1 - m1 - uh[1] * m2);
 }
 
-__global__ void __launch_bounds__(256) lstm_bwd_kernel(float* __restrict__ z, const float* __restrict__ c_prev,
+__global__ void __launch_bounds__(256, 3) lstm_bwd_kernel(float* __restrict__ z, const float* __restrict__ c_prev,
                                                        const float* __restrict__ g_h, float* __restrict__ g_c,
                                                        int64_t n_rows, const float* __restrict__ params,
                                                        float* __restrict__ grads, const LnOffsets off) {
@@ -410,13 +410,23 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(float* __restrict__ z, co
       z[row * 256 + g * 64 + lane + 32] = du[1];
     }
   }
+  // LayerNorm parameter gradients: summed over the CTA's warps in shared memory, then one global
+  // atomic per parameter and CTA (640 addresses would otherwise serialise every warp of the grid)
+  __shared__ float red[2 * 5 * 64];
+  for (int i = threadIdx.x; i < 2 * 5 * 64; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int g = 0; g < 5; ++g)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      atomicAdd(grads + off.gamma[g] + lane + 32 * q, dgam[g][q]);
-      atomicAdd(grads + off.beta[g] + lane + 32 * q, dbet[g][q]);
+      atomicAdd(red + g * 64 + lane + 32 * q, dgam[g][q]);
+      atomicAdd(red + 320 + g * 64 + lane + 32 * q, dbet[g][q]);
     }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 5 * 64; i += blockDim.x) {
+    const int g = (i % 320) >> 6, col = i & 63;
+    atomicAdd(grads + (i < 320 ? off.gamma[g] : off.beta[g]) + col, red[i]);
+  }
 }
 
 // ------------------------------------------------------------------------------------

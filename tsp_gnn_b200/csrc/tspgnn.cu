@@ -724,14 +724,14 @@ extern "C" int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const fl
   } else {
     CUDA_TRY(cudaMemsetAsync(h->xV, 0, h->nV_pad * D * 4, s));
     if (h->hp == 2) {
-      tc_edge_init_kernel<2><<<h->tilesE, TILE_ROWS, 0, s>>>(dW, dC, h->nE, h->stateE);
+      tc_edge_init_kernel<2><<<h->tilesE, TILE_ROWS, 0, s>>>(dW, dC, h->d_params + h->po.einit_w[0], h->nE, h->stateE);
       LAUNCH_CHECK(h);
       tc_pack_state_kernel<2><<<grid_for(h->nV_pad * 32, 256), 256, 0, s>>>(h->Vh, nullptr, h->nV, h->nV_pad, h->stateV);
       LAUNCH_CHECK(h);
       tc_zero_c_kernel<2><<<grid_for(h->nV_pad * 16, 256), 256, 0, s>>>(h->nV_pad, h->stateV);
       LAUNCH_CHECK(h);
     } else {
-      tc_edge_init_kernel<1><<<h->tilesE, TILE_ROWS, 0, s>>>(dW, dC, h->nE, h->stateE);
+      tc_edge_init_kernel<1><<<h->tilesE, TILE_ROWS, 0, s>>>(dW, dC, h->d_params + h->po.einit_w[0], h->nE, h->stateE);
       LAUNCH_CHECK(h);
       tc_pack_state_kernel<1><<<grid_for(h->nV_pad * 32, 256), 256, 0, s>>>(h->Vh, nullptr, h->nV, h->nV_pad, h->stateV);
       LAUNCH_CHECK(h);
