@@ -210,10 +210,18 @@ struct XtdyArgs {
 };
 
 constexpr int XT_ROWS = 64;
+constexpr int XT_SMEM_BYTES = 2 * 2 * XT_ROWS * 64 * 4;   // two stages x (X chunk, dY chunk)
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t saddr, const void* gptr, bool valid) {
+  // 16-byte asynchronous copy global -> shared; src-size 0 zero-fills the destination (rows past the end)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(256) xtdy_kernel(const XtdyArgs a) {
-  __shared__ __align__(16) float Xs[XT_ROWS][64];
-  __shared__ __align__(16) float Ys[XT_ROWS][64];
+  extern __shared__ __align__(16) float xt_smem[];   // [stage][X | dY][64 rows][64]
   const int tid = threadIdx.x;
   const int g = tid >> 6, t = tid & 63;
   const int ty = t >> 3, tx = t & 7;
@@ -229,36 +237,39 @@ __global__ void __launch_bounds__(256) xtdy_kernel(const XtdyArgs a) {
   float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const bool do_bias = (a.db != nullptr) && kb == 0 && ty == 0;
   const int64_t n_chunks = (a.n_rows + XT_ROWS - 1) / XT_ROWS;
-  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+  const uint32_t smem_s = ptx::smem_u32(xt_smem);
+  // stage `st` <- chunk `ch`: 64 rows x 16 float4 per matrix, four asynchronous 16-byte copies per thread and matrix
+  auto prefetch = [&](int64_t ch, int st) {
     const int64_t row0 = ch * XT_ROWS;
-    __syncthreads();
-    // 64 rows x 16 float4 per matrix: four per thread and matrix, all loads in flight before the stores
-    float4 xv[4], yv[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int i = tid + q * 256;
       const int r = i >> 4, c4 = i & 15;
-      xv[q] = yv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < a.n_rows) {
-        xv[q] = *reinterpret_cast<const float4*>(xp + (row0 + r) * xld + c4 * 4);
-        yv[q] = *reinterpret_cast<const float4*>(yp + (row0 + r) * a.dyld + c4 * 4);
-      }
+      const bool valid = row0 + r < a.n_rows;
+      const int64_t row = valid ? row0 + r : 0;
+      const uint32_t dst = smem_s + ((st * 2) * XT_ROWS * 64 + r * 64 + c4 * 4) * 4;
+      cp_async16_zfill(dst, xp + row * xld + c4 * 4, valid);
+      cp_async16_zfill(dst + XT_ROWS * 64 * 4, yp + row * a.dyld + c4 * 4, valid);
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int i = tid + q * 256;
-      const int r = i >> 4, c4 = i & 15;
-      *reinterpret_cast<float4*>(&Xs[r][c4 * 4]) = xv[q];
-      *reinterpret_cast<float4*>(&Ys[r][c4 * 4]) = yv[q];
-    }
+    cp_async_commit();
+  };
+  int64_t ch = blockIdx.x;
+  if (ch < n_chunks) prefetch(ch, 0);
+  for (int it = 0; ch < n_chunks; ch += gridDim.x, ++it) {
+    const int st = it & 1;
+    const bool more = ch + gridDim.x < n_chunks;
+    if (more) prefetch(ch + gridDim.x, st ^ 1);      // overlaps the math of this chunk
+    if (more) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    const float* Xs = xt_smem + (st * 2) * XT_ROWS * 64;
+    const float* Ys = Xs + XT_ROWS * 64;
 #pragma unroll 4
     for (int rr = 0; rr < XT_ROWS / 4; ++rr) {
       const int r = rr * 4 + g;
-      const float4 x0 = *reinterpret_cast<const float4*>(&Xs[r][ty * 8]);
-      const float4 x1 = *reinterpret_cast<const float4*>(&Xs[r][ty * 8 + 4]);
-      const float4 y0 = *reinterpret_cast<const float4*>(&Ys[r][tx * 4]);
-      const float4 y1 = *reinterpret_cast<const float4*>(&Ys[r][32 + tx * 4]);
+      const float4 x0 = *reinterpret_cast<const float4*>(Xs + r * 64 + ty * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(Xs + r * 64 + ty * 8 + 4);
+      const float4 y0 = *reinterpret_cast<const float4*>(Ys + r * 64 + tx * 4);
+      const float4 y1 = *reinterpret_cast<const float4*>(Ys + r * 64 + 32 + tx * 4);
       const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
 #pragma unroll
@@ -270,13 +281,12 @@ __global__ void __launch_bounds__(256) xtdy_kernel(const XtdyArgs a) {
         for (int j = 0; j < 8; ++j) bs[j] += ya[j];
       }
     }
+    __syncthreads();   // this stage is overwritten by the prefetch issued in the next iteration
   }
   // sum the four row groups in shared memory (re-using the staging buffers), then one atomic per element
-  __syncthreads();
-  float* red = &Xs[0][0];     // [64][64]
-  float* redb = &Ys[0][0];    // [64]
-  for (int i = tid; i < 64 * 64; i += 256) red[i] = 0.f;
-  if (tid < 64) redb[tid] = 0.f;
+  float* red = xt_smem;                 // [64][64]
+  float* redb = xt_smem + 64 * 64;      // [64]
+  for (int i = tid; i < 64 * 64 + 64; i += 256) red[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 8; ++i)
