@@ -16,6 +16,12 @@ Design: deferred evaluation.  Every op returns a ``Tensor`` holding a closure; `
 evaluates closures against the feed dict.  ``while_loop`` runs as a Python loop at evaluation
 time, calling the reference's body function on constant tensors each iteration.
 Use ``install()`` to register the module and ``reset()`` between graphs.
+
+``reset(backend="torch")`` evaluates the same closures on float64 torch tensors, which gives the
+reference's training graph (model.py:157-167) something to differentiate: ``tf.gradients`` becomes
+``torch.autograd.grad`` over the graph the reference's code built, ``tf.clip_by_global_norm`` and
+``tf.train.AdamOptimizer`` are restated from the TF 1.x sources ("TF:" comments), and the gradients
+/ Adam slots of the last step can be read back with ``last_gradients()`` / ``optimizer_slots()``.
 """
 import sys
 import types
@@ -26,12 +32,80 @@ import numpy as np
 float32 = np.float32
 int32 = np.int32
 
-_STATE = {"scope": [], "variables": {}, "trainable": [], "dtype": np.float64, "env": None, "init_rng": None}
+_STATE = {"scope": [], "variables": {}, "trainable": [], "dtype": np.float64, "env": None, "init_rng": None,
+          "backend": "numpy"}
 
 
-def reset(dtype=np.float64, seed=0):
+def reset(dtype=np.float64, seed=0, backend="numpy"):
     _STATE.update(scope=[], variables={}, trainable=[], assertions=[], dtype=dtype, env=None,
-                  init_rng=np.random.RandomState(seed))
+                  init_rng=np.random.RandomState(seed), backend=backend, last_grads={}, adam={})
+
+
+# ----------------------------------------------------------------------------------------
+# array backend: numpy (default) or float64 torch tensors (differentiable)
+# ----------------------------------------------------------------------------------------
+def _torch_mode():
+    return _STATE.get("backend") == "torch"
+
+
+def _T():
+    import torch
+    return torch
+
+
+def _is_t(a):
+    return _torch_mode() and isinstance(a, _T().Tensor)
+
+
+def _farr(a):
+    """value -> float array of the working dtype"""
+    if _torch_mode():
+        t = _T()
+        return a.to(t.float64) if isinstance(a, t.Tensor) else t.as_tensor(np.asarray(a, dtype=np.float64))
+    return np.asarray(a).astype(_STATE["dtype"])
+
+
+def _iarr(a):
+    if _torch_mode():
+        t = _T()
+        return a.to(t.int64) if isinstance(a, t.Tensor) else t.as_tensor(np.asarray(a).astype(np.int64))
+    return np.asarray(a).astype(np.int64)
+
+
+def _cat(xs, axis):
+    return _T().cat(list(xs), dim=axis) if _torch_mode() else np.concatenate(list(xs), axis=axis)
+
+
+def _mean(a, axis=None, keepdims=False):
+    if _is_t(a):
+        return a.mean() if axis is None else a.mean(dim=axis, keepdim=keepdims)
+    return np.mean(a) if axis is None else a.mean(axis=axis, keepdims=keepdims)
+
+
+def _sum(a):
+    return a.sum() if _is_t(a) else np.sum(a)
+
+
+def _fn(name, a):
+    """elementwise sqrt / exp / abs / log1p / round / square"""
+    if _is_t(a):
+        return getattr(_T(), name)(a)
+    return getattr(np, name)(a)
+
+
+def _relu_v(a):
+    return _T().clamp(a, min=0) if _is_t(a) else np.maximum(a, 0)
+
+
+def _sigmoid_v(a):
+    e = _fn("exp", -_fn("abs", a))
+    if _is_t(a):
+        return _T().where(a >= 0, 1.0 / (1.0 + e), e / (1.0 + e))
+    return np.where(a >= 0, 1.0 / (1.0 + e), e / (1.0 + e))
+
+
+def _shape_of(a):
+    return tuple(a.shape) if hasattr(a, "shape") else np.shape(a)
 
 
 # ----------------------------------------------------------------------------------------
@@ -88,10 +162,8 @@ class Placeholder(Tensor):
         env = _STATE["env"]
         if self not in env["feed"]:
             raise ValueError("You must feed a value for placeholder tensor %r" % self.name)
-        a = np.asarray(env["feed"][self])
-        if self.dtype is float32:
-            return a.astype(_STATE["dtype"])
-        return a.astype(np.int64)
+        a = env["feed"][self]
+        return _farr(a) if self.dtype is float32 else _iarr(a)
 
     __hash__ = Tensor.__hash__
     __eq__ = Tensor.__eq__
@@ -106,7 +178,12 @@ class Variable(Tensor):
         store = _STATE["variables"]
         if self.name not in store:
             store[self.name] = np.asarray(self._init_fn())
-        return store[self.name].astype(_STATE["dtype"])
+        if _torch_mode():
+            t = _T()
+            if not isinstance(store[self.name], t.Tensor):      # leaf tensor: gradients flow to the variable
+                store[self.name] = t.tensor(np.asarray(store[self.name], dtype=np.float64), requires_grad=True)
+            return store[self.name]
+        return np.asarray(store[self.name]).astype(_STATE["dtype"])
 
     __hash__ = Tensor.__hash__
     __eq__ = Tensor.__eq__
@@ -192,15 +269,15 @@ def placeholder(dtype, shape=None, name=None):
 
 
 def shape(x):
-    return Tensor(lambda: np.array(np.shape(_v(x)), dtype=np.int64))
+    return Tensor(lambda: np.array(_shape_of(_v(x)), dtype=np.int64))
 
 
 def zeros_like(x, dtype=None):
-    return Tensor(lambda: np.zeros_like(_v(x)))
+    return Tensor(lambda: _v(x) * 0)
 
 
 def ones_like(x):
-    return Tensor(lambda: np.ones_like(_v(x)))
+    return Tensor(lambda: _v(x) * 0 + 1)
 
 
 def matmul(a, b, adjoint_a=False, **k):
@@ -208,7 +285,7 @@ def matmul(a, b, adjoint_a=False, **k):
 
 
 def concat(values, axis=0):
-    return Tensor(lambda: np.concatenate([_v(t) for t in values], axis=axis))
+    return Tensor(lambda: _cat([_v(t) for t in values], axis))
 
 
 def less(a, b):
@@ -216,7 +293,10 @@ def less(a, b):
 
 
 def tile(x, multiples):
-    return Tensor(lambda: np.tile(_v(x), [int(_v(m)) for m in multiples]))
+    def ev():
+        a, reps = _v(x), [int(_v(m)) for m in multiples]
+        return a.repeat(*reps) if _is_t(a) else np.tile(a, reps)
+    return Tensor(ev)
 
 
 def div(a, b):
@@ -224,33 +304,32 @@ def div(a, b):
 
 
 def sqrt(x):
-    return Tensor(lambda: np.sqrt(_v(x)))
+    return Tensor(lambda: _fn("sqrt", _v(x)))
 
 
 def cast(x, dtype):
     if dtype is float32:
-        return Tensor(lambda: np.asarray(_v(x)).astype(_STATE["dtype"]))
-    return Tensor(lambda: np.asarray(_v(x)).astype(np.int64))
+        return Tensor(lambda: _farr(_v(x)))
+    return Tensor(lambda: _iarr(_v(x)))
 
 
 def reshape(x, shp):
-    return Tensor(lambda: np.reshape(_v(x), shp))
+    def ev():
+        a = _v(x)
+        return a.reshape(tuple(shp)) if _is_t(a) else np.reshape(a, shp)
+    return Tensor(ev)
 
 
 def reduce_mean(x, **k):
-    return Tensor(lambda: np.mean(_v(x)))
+    return Tensor(lambda: _mean(_v(x)))
 
 
 def reduce_sum(x, **k):
-    return Tensor(lambda: np.sum(_v(x)))
+    return Tensor(lambda: _sum(_v(x)))
 
 
 def sigmoid(x):
-    def ev():
-        a = _v(x)
-        e = np.exp(-np.abs(a))
-        return np.where(a >= 0, 1.0 / (1.0 + e), e / (1.0 + e))
-    return Tensor(ev)
+    return Tensor(lambda: _sigmoid_v(_v(x)))
 
 
 def multiply(a, b):
@@ -266,7 +345,7 @@ def not_equal(a, b):
 
 
 def round(x):  # noqa: A001  (TF: round half to even, like numpy)
-    return Tensor(lambda: np.round(_v(x)))
+    return Tensor(lambda: _fn("round", _v(x)))
 
 
 def add_n(xs):
@@ -275,7 +354,10 @@ def add_n(xs):
 
 def assert_equal(a, b, data=None, message=None, **k):
     def ev():
-        if not np.all(np.asarray(_v(a)) == np.asarray(_v(b))):
+        va, vb = _v(a), _v(b)
+        va = va.detach().numpy() if _is_t(va) else va
+        vb = vb.detach().numpy() if _is_t(vb) else vb
+        if not np.all(np.asarray(va) == np.asarray(vb)):
             raise errors.InvalidArgumentError(message)
         return True
     t = Tensor(ev)
@@ -284,15 +366,46 @@ def assert_equal(a, b, data=None, message=None, **k):
 
 
 def gradients(ys, xs, **k):
-    return [Tensor(lambda: (_ for _ in ()).throw(NotImplementedError("tf.gradients is not emulated"))) for _ in xs]
+    """TF: tf.gradients(ys, xs) -- here torch.autograd.grad over the graph the reference built (torch backend)."""
+    xs = list(xs)
+
+    def all_grads():
+        if not _torch_mode():
+            raise NotImplementedError("tf.gradients needs tf1_shim.reset(backend='torch')")
+        y = _v(ys)
+        leaves = [_v(x) for x in xs]
+        gs = _T().autograd.grad(y, leaves, allow_unused=True)
+        out = [g if g is not None else leaves[i] * 0 for i, g in enumerate(gs)]
+        _STATE["last_grads"] = {x.name: g.detach().numpy().copy() for x, g in zip(xs, out)}
+        return out
+    whole = Tensor(all_grads)
+    return [Tensor(lambda i=i: _v(whole)[i]) for i in range(len(xs))]
 
 
 def clip_by_global_norm(grads, clip):
-    return grads, None
+    """TF: global_norm = sqrt(sum_i ||g_i||^2); every g_i is scaled by clip / max(global_norm, clip)."""
+    grads = list(grads)
+
+    def norm():
+        return _fn("sqrt", sum(_sum(_fn("square", _v(g))) for g in grads))
+    gn = Tensor(norm)
+
+    def scaled(i):
+        n = _v(gn)
+        nv = float(n.detach()) if _is_t(n) else float(n)
+        _STATE["last_global_norm"] = nv
+        return _v(grads[i]) * (float(_v(clip)) / max(nv, float(_v(clip))))
+    return [Tensor(lambda i=i: scaled(i)) for i in range(len(grads))], gn
 
 
 def while_loop(cond, body, loop_vars, **k):
     scope_at_build = list(_STATE["scope"])      # TF traces the body here, under the current scopes
+    try:
+        # TF builds the loop body ONCE at graph-construction time, which is when its variables come into
+        # existence (model.py:166 lists tf.trainable_variables() right after); the result is discarded
+        body(*loop_vars)
+    except Exception:
+        pass                                     # bodies that need concrete values (TensorArray.write) create no variables
 
     def ev():
         saved, _STATE["scope"] = _STATE["scope"], list(scope_at_build)
@@ -343,7 +456,10 @@ class TensorArray(object):
         return new
 
     def stack(self):
-        return Tensor(lambda: np.array([self.items[k] for k in sorted(self.items)]))
+        def ev():
+            vals = [self.items[k] for k in sorted(self.items)]
+            return _T().stack(vals) if _torch_mode() else np.array(vals)
+        return Tensor(ev)
 
 
 class _LoopArray(object):
@@ -366,7 +482,7 @@ class LSTMStateTuple(object):
 # layers / cells (TF-internal arithmetic, restated)
 # ----------------------------------------------------------------------------------------
 def _relu(x):
-    return Tensor(lambda: np.maximum(_v(x), 0))
+    return Tensor(lambda: _relu_v(_v(x)))
 
 
 class _Dense(object):
@@ -384,7 +500,7 @@ class _Dense(object):
         if self.kernel is None:
             with variable_scope(self.name):
                 ki, bi, units = self.kernel_initializer, self.bias_initializer, self.units
-                self.kernel = _make_variable("kernel", lambda: ki((np.shape(_v(x))[1], units)))
+                self.kernel = _make_variable("kernel", lambda: ki((_shape_of(_v(x))[1], units)))
                 self.bias = _make_variable("bias", lambda: bi((units,)))
         kern, bias, act = self.kernel, self.bias, self.activation
         y = Tensor(lambda: _v(x) @ _v(kern) + (_v(bias) if self.use_bias else 0))
@@ -393,9 +509,9 @@ class _Dense(object):
 
 def _layer_norm(u, gamma, beta):
     # TF: contrib.layers.layer_norm(begin_norm_axis=1): nn.moments + nn.batch_normalization, eps 1e-12
-    mean = u.mean(axis=1, keepdims=True)
-    var = np.square(u - mean).mean(axis=1, keepdims=True)
-    inv = (1.0 / np.sqrt(var + u.dtype.type(1e-12))) * gamma
+    mean = _mean(u, axis=1, keepdims=True)
+    var = _mean(_fn("square", u - mean), axis=1, keepdims=True)
+    inv = (1.0 / _fn("sqrt", var + 1e-12)) * gamma
     return u * inv + (beta - mean * inv)
 
 
@@ -415,7 +531,7 @@ class _LayerNormBasicLSTMCell(object):
         d = self.num_units
         with variable_scope("layer_norm_basic_lstm_cell"):
             xavier = _xavier_initializer()
-            vs = {"kernel": _make_variable("kernel", lambda: xavier((np.shape(_v(inputs))[1] + d, 4 * d)))}
+            vs = {"kernel": _make_variable("kernel", lambda: xavier((_shape_of(_v(inputs))[1] + d, 4 * d)))}
             for g in ("input", "transform", "forget", "output", "state"):
                 with variable_scope(g):
                     vs[g + "/gamma"] = _make_variable("gamma", lambda: np.ones(d))
@@ -424,7 +540,7 @@ class _LayerNormBasicLSTMCell(object):
 
         def ev():
             c, h = _v(state.c), _v(state.h)
-            z = np.concatenate([_v(inputs), h], axis=1) @ _v(vs["kernel"])
+            z = _cat([_v(inputs), h], 1) @ _v(vs["kernel"])
             i, j, f, o = z[:, :d], z[:, d:2 * d], z[:, 2 * d:3 * d], z[:, 3 * d:]
             ln = lambda u, s: _layer_norm(u, _v(vs[s + "/gamma"]), _v(vs[s + "/beta"]))
             i, j, f, o = ln(i, "input"), ln(j, "transform"), ln(f, "forget"), ln(o, "output")
@@ -441,15 +557,42 @@ class _LayerNormBasicLSTMCell(object):
 
 def _sigmoid_cross_entropy_with_logits(labels=None, logits=None):
     # TF: max(x, 0) - x*z + log(1 + exp(-|x|))
-    return Tensor(lambda: np.maximum(_v(logits), 0) - _v(logits) * _v(labels) + np.log1p(np.exp(-np.abs(_v(logits)))))
+    return Tensor(lambda: _relu_v(_v(logits)) - _v(logits) * _v(labels)
+                  + _fn("log1p", _fn("exp", -_fn("abs", _v(logits)))))
 
 
 class _Adam(object):
-    def __init__(self, **k):
-        pass
+    """TF: tf.train.AdamOptimizer(learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8)._apply_dense:
+    lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t); m = beta1 m + (1-beta1) g; v = beta2 v + (1-beta2) g^2;
+    var -= lr_t * m / (sqrt(v) + epsilon).  The update is committed after every fetch of the same
+    Session.run has been evaluated, so loss / predictions fetched alongside are pre-update values."""
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, **k):
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta1, beta2, epsilon
 
     def apply_gradients(self, gv):
-        return Tensor(lambda: (_ for _ in ()).throw(NotImplementedError("train_step is not emulated")))
+        gv = list(gv)
+
+        def ev():
+            st = _STATE["adam"]
+            grads = [(_v(g), v) for g, v in gv]
+            st["t"] = st.get("t", 0) + 1
+            t = st["t"]
+            lr_t = self.lr * np.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+            updates = {}
+            for g, var in grads:
+                g = g.detach().numpy() if _is_t(g) else np.asarray(g)
+                m = st.setdefault("m", {}).get(var.name, np.zeros_like(g))
+                vv = st.setdefault("v", {}).get(var.name, np.zeros_like(g))
+                m = self.b1 * m + (1 - self.b1) * g
+                vv = self.b2 * vv + (1 - self.b2) * g * g
+                st["m"][var.name], st["v"][var.name] = m, vv
+                cur = _v(var)
+                cur = cur.detach().numpy() if _is_t(cur) else np.asarray(cur)
+                updates[var.name] = cur - lr_t * m / (np.sqrt(vv) + self.eps)
+            _STATE["env"].setdefault("post", []).append(lambda: set_variables(updates))
+            return None
+        return Tensor(ev)
 
 
 class errors(object):
@@ -481,9 +624,24 @@ class Session(object):
                 if isinstance(f, LSTMStateTuple):
                     return LSTMStateTuple(c=ev(f.c), h=ev(f.h))
                 return _v(f)
-            return ev(fetches)
+            out = ev(fetches)
+            for commit in _STATE["env"].get("post", []):
+                commit()
+            return _to_numpy(out)
         finally:
             _STATE["env"] = None
+
+
+def _to_numpy(x):
+    if isinstance(x, list):
+        return [_to_numpy(v) for v in x]
+    if isinstance(x, dict):
+        return {k: _to_numpy(v) for k, v in x.items()}
+    if isinstance(x, LSTMStateTuple):
+        return LSTMStateTuple(c=_to_numpy(x.c), h=_to_numpy(x.h))
+    if _torch_mode() and isinstance(x, _T().Tensor):
+        return x.detach().numpy()
+    return x
 
 
 def global_variables_initializer():
@@ -493,6 +651,27 @@ def global_variables_initializer():
 def set_variables(values):
     """name -> array; names are the TF variable names the reference's scopes produced."""
     _STATE["variables"].update({k: np.asarray(v) for k, v in values.items()})
+
+
+def get_variables():
+    out = {}
+    for k, v in _STATE["variables"].items():
+        out[k] = v.detach().numpy().copy() if _torch_mode() and isinstance(v, _T().Tensor) else np.asarray(v).copy()
+    return out
+
+
+def last_gradients():
+    """name -> d(loss + l2 * vars_cost)/d(variable) of the last evaluated tf.gradients (before clipping)."""
+    return dict(_STATE.get("last_grads", {}))
+
+
+def last_global_norm():
+    return _STATE.get("last_global_norm")
+
+
+def optimizer_slots():
+    st = _STATE.get("adam", {})
+    return {"step": st.get("t", 0), "m": dict(st.get("m", {})), "v": dict(st.get("v", {}))}
 
 
 def variable_names():
@@ -507,7 +686,7 @@ def install():
         rnn=types.SimpleNamespace(LayerNormBasicLSTMCell=_LayerNormBasicLSTMCell, LSTMStateTuple=LSTMStateTuple))
     me.contrib = contrib
     me.nn = types.SimpleNamespace(relu=_relu, sigmoid_cross_entropy_with_logits=_sigmoid_cross_entropy_with_logits,
-                                  l2_loss=lambda v: Tensor(lambda: np.sum(np.square(_v(v))) / 2))
+                                  l2_loss=lambda v: Tensor(lambda: _sum(_fn("square", _v(v))) / 2))
     me.layers = types.SimpleNamespace(Dense=_Dense)
     me.train = types.SimpleNamespace(AdamOptimizer=_Adam)
     sys.modules["tensorflow"] = me

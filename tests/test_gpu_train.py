@@ -112,6 +112,43 @@ def test_gradients_match_oracle_config1():
     check_grads(blob, ref["grads"], GRAD_RTOL["bf16x3"], label="config1")
 
 
+@pytest.mark.parametrize("mode", ["simt", "bf16x3"])
+@pytest.mark.parametrize("name", ["ref_train_tiny", "ref_train_sparse"])
+def test_train_step_matches_reference_training_graph_fixtures(name, mode):
+    """The CUDA training step against fixtures produced by the reference's OWN training graph
+    (/root/reference/model.py:157-167, run unmodified on oracle/tf1_shim.py's torch backend by
+    tests/golden/make_reference_golden.py): loss, predictions, the clipped gradient (read back as Adam's
+    first moment, m = 0.1 * g_clipped after one step from zero slots) and the updated variables."""
+    import test_reference_shim as trs
+    from tsp_gnn_b200.engine import Engine
+    EV, W, C, y, nv, ne, params, T, n_steps = trs.train_inputs(name)
+    eng = Engine(64, mode, 0)
+    eng.set_params(params)                      # hyper-parameters stay at the reference's (model.py:13-15)
+    eng.plan(nv, ne, EV.src, EV.dst)
+    loss, logits, preds = eng.train_step_host(W, C, y, T)
+    assert abs(loss - trs.TRAIN[name + "/loss_0"]) < 1e-5
+    assert np.abs(preds - trs.TRAIN[name + "/predictions_0"]).max() < 1e-4
+    gold = trs.train_fixture(name, "grad_0")
+    gnorm = float(trs.TRAIN[name + "/global_norm_0"])
+    m_ref = P.flatten({k: (0.1 * v * (0.65 / max(gnorm, 0.65))).astype(np.float32) for k, v in gold.items()})
+    m_got = eng.get_optimizer_state()["m"]
+    rtol = GRAD_RTOL[mode]
+    names = [n for n, _, _ in P.param_spec(64)]
+    got_m, ref_m = P.unflatten(m_got), P.unflatten(m_ref)
+    bad = {k: float(np.abs(got_m[k] - ref_m[k]).max() / (np.abs(ref_m[k]).max() + 1e-30)) for k in names
+           if np.abs(got_m[k] - ref_m[k]).max() > rtol * np.abs(ref_m[k]).max() + 1e-12}
+    assert not bad, bad
+    # variables after the step, in units of the learning rate (fixture stored to 1e-3 of a step)
+    got = P.unflatten(eng.get_params())
+    dv_ref = trs.train_fixture(name, "dvar_over_lr_0")
+    diffs = np.concatenate([np.abs((got[k].astype(np.float64) - params[k]) / 2e-5 - dv_ref[k].astype(np.float64)).reshape(-1)
+                            for k in names])
+    print("%s %s |d var| / lr vs reference graph: quantiles 50/90/99/100 %% %s" %
+          (name, mode, np.quantile(diffs, [0.5, 0.9, 0.99, 1.0])))
+    assert np.quantile(diffs, 0.9) < 0.05 and diffs.max() < 2.5      # Adam amplifies tiny gradients, see above
+    eng.close()
+
+
 def test_sharded_gradients_add_up():
     """two shards, each with the global batch as divisor, sum to the batch gradient."""
     from tsp_gnn_b200.engine import Engine
