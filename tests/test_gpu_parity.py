@@ -144,6 +144,36 @@ def test_batch_members_are_independent_at_full_size(mode):
     assert np.abs(sub["predictions"] - ref["predictions"]).max() <= TOL_PRED[mode]
 
 
+def test_config4_mixed_512_and_config5_large_instances_at_full_size():
+    """BASELINE config 4 (512 instances, n in 20..60, 32 timesteps; one GPU's view of the whole batch) and
+    config 5 (n = 160 and 320, 32 timesteps) at their full sizes, where the float64 oracle for the whole batch
+    would take many minutes: instances are independent blocks (instance_loader.py:56-66), so members picked
+    from the big batch must reproduce the oracle's predictions for those members alone."""
+    params = orc.init_params(64, seed=3, perturb_ln=True)
+    # config 4
+    sizes = inst.mixed_sizes(512, 20, 60, seed=11)
+    insts = inst.synth_instances(sizes, seed=300, two_opt_sweeps=0)
+    EV, W, C, y, nv, ne = inst.create_batch(insts)
+    got = run_engine("bf16x3", params, EV, W, C, nv, ne, 32)
+    assert np.isfinite(got["predictions"]).all() and got["predictions"].shape == (512,)
+    eoff = np.concatenate([[0], np.cumsum(ne)])
+    for k in (0, 255, 511):
+        EVs, Ws, _, _, nvs, nes = inst.create_batch([insts[k]])
+        ref = orc.forward(params, EVs.src, EVs.dst, Ws, C[eoff[k]:eoff[k + 1]], nvs, nes, 32)
+        assert abs(got["predictions"][k] - ref["predictions"][0]) <= TOL_PRED["bf16x3"], k
+    # config 5: one n=160 and one n=320 instance inside a batch of large instances
+    big = inst.synth_instances([320, 160, 80, 160], seed=500, two_opt_sweeps=0)
+    EV, W, C, y, nv, ne = inst.create_batch(big)
+    got = run_engine("bf16x3", params, EV, W, C, nv, ne, 32)
+    eoff = np.concatenate([[0], np.cumsum(ne)])
+    for k in (0, 1):
+        EVs, Ws, _, _, nvs, nes = inst.create_batch([big[k]])
+        ref = orc.forward(params, EVs.src, EVs.dst, Ws, C[eoff[k]:eoff[k + 1]], nvs, nes, 32)
+        err = abs(got["predictions"][k] - ref["predictions"][0])
+        print("config 5 member n=%d pred err %.2e" % (nv[k], err))
+        assert err <= TOL_PRED["bf16x3"], k
+
+
 def test_session_drop_in_surface_with_dense_ev():
     import tsp_gnn_b200 as tg
     EV, W, C, y, nv, ne = inst.synth_batch([8, 9, 7, 10], seed=6)

@@ -807,7 +807,7 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
           const int rr = 2 * i + hw;
           const int s = __shfl_sync(0xffffffffu, my_s, rr);
           const int d = __shfl_sync(0xffffffffu, my_d, rr);
-          if (s >= 0 && !(a.fold & 2)) {
+          if (s >= 0) {
             const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
             ptx::red_add_v4(a.xV + static_cast<int64_t>(d) * D + 4 * c16, m);
             if (s != cur_s) {
@@ -931,12 +931,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   if (warp < 4 * K2_CHAINS) {
     if (a.vote_mode) k2_chain<HP, 2>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
     else if (is_v) k2_chain<HP, 0>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
-    else if (a.fold & 1) k2_chain<HP, 3>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
+    else if (a.fold) k2_chain<HP, 3>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
     else k2_chain<HP, 1>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);
   } else if (warp == 12) {
     if (ntiles > 0)
       k2_mma<HP>(wsm, slots, bar_w, slot_full, acc_full, act_ready, tmem, ntiles,
-                 (a.vote_mode || ((a.fold & 1) && !is_v)) ? 3 : 4, a.timeline);
+                 (a.vote_mode || (a.fold && !is_v)) ? 3 : 4, a.timeline);
   } else if (warp == 13) {
     if (lane == 0) {
       for (int n = 0; n < ntiles; ++n) {

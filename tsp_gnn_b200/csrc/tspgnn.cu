@@ -6,7 +6,6 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -610,8 +609,6 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, lon
   K2Args a;
   a.timeline = timeline;
   a.fold = (fold && !vote) ? 1 : 0;
-  static const bool no_scatter = getenv("TSPGNN_DEBUG_NOSCATTER") != nullptr;   // timing experiment only: results are wrong
-  if (no_scatter) a.fold |= 2;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = vote ? h->d_wmlp[2] : h->d_wmlp[1];
