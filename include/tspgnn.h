@@ -61,7 +61,9 @@ int tspgnn_set_params(tspgnn_handle h, const float* host_blob, int64_t n_floats)
  * instance_loader.py:45-67): edge row e has its two non-zeros in columns edge_src[e] <
  * edge_dst[e] (global vertex ids); instance k owns edge rows [sum n_edges[:k], +n_edges[k])
  * and vertex ids [sum n_vertices[:k], +n_vertices[k]).  Host pointers; copied to the device
- * (inside the call) together with the derived CSR of EV^T.  Workspace is (re)allocated here. */
+ * (inside the call) together with the derived CSR of EV^T.  Workspace is (re)allocated here.  Rows are
+ * validated like graphnn.check_run (block-diagonal structure); a batch that fails leaves the handle
+ * WITHOUT a plan (TSPGNN_E_INVALID, message names the offending row), the previous one is gone. */
 int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_vertices, const int32_t* n_edges,
                 const int32_t* edge_src, const int32_t* edge_dst);
 

@@ -434,44 +434,6 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
   }
   if (nE >= (int64_t(1) << 31) / 2 || nV >= (int64_t(1) << 31)) return fail(TSPGNN_E_INVALID, "batch too large for int32 ids");
   if (!edge_src || !edge_dst) return fail(TSPGNN_E_INVALID, "edge_src / edge_dst is NULL");
-  // every edge row must connect two distinct vertices of its own instance: this is the
-  // block-diagonal structure of EV (instance_loader.py:56-66), checked like graphnn.check_run.
-  // CSR of EV^T (edge rows incident to every vertex): only the fp32 SIMT path segment-sums with it,
-  // the tensor-core path scatters from the edge side.
-  const bool need_csr = (h->hp == 0);
-  std::vector<int32_t> vptr(need_csr ? nV + 1 : 1, 0);
-  for (int k = 0; k < n_instances; ++k) {
-    // branch-free pass (unsigned range checks vectorise); the offending row is located only on failure
-    const uint32_t lo = static_cast<uint32_t>(voff[k]), span = static_cast<uint32_t>(voff[k + 1] - voff[k]);
-    uint32_t bad = 0;
-    for (int64_t e = eoff[k]; e < eoff[k + 1]; ++e) {
-      const uint32_t s = static_cast<uint32_t>(edge_src[e]) - lo, t = static_cast<uint32_t>(edge_dst[e]) - lo;
-      bad |= static_cast<uint32_t>(s >= span) | static_cast<uint32_t>(t >= span) | static_cast<uint32_t>(s == t);
-    }
-    if (bad)
-      for (int64_t e = eoff[k]; e < eoff[k + 1]; ++e) {
-        const int64_t s = edge_src[e], t = edge_dst[e];
-        if (s < voff[k] || s >= voff[k + 1] || t < voff[k] || t >= voff[k + 1] || s == t)
-          return fail(TSPGNN_E_INVALID,
-                      "Matrix EV: edge row %lld connects columns (%lld,%lld) outside instance %d's vertex range [%lld,%lld)",
-                      (long long)e, (long long)s, (long long)t, k, (long long)voff[k], (long long)voff[k + 1]);
-      }
-    if (need_csr)
-      for (int64_t e = eoff[k]; e < eoff[k + 1]; ++e) {
-        vptr[edge_src[e] + 1]++;
-        vptr[edge_dst[e] + 1]++;
-      }
-  }
-  std::vector<int32_t> vidx;
-  if (need_csr) {
-    for (int64_t v = 0; v < nV; ++v) vptr[v + 1] += vptr[v];
-    vidx.resize(2 * nE);
-    std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
-    for (int64_t e = 0; e < nE; ++e) {
-      vidx[fill[edge_src[e]]++] = static_cast<int32_t>(e);
-      vidx[fill[edge_dst[e]]++] = static_cast<int32_t>(e);
-    }
-  }
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaDeviceSynchronize());
   const int64_t nE_pad = (nE + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
@@ -521,14 +483,59 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
   }
   CUDA_TRY(cudaMemcpyAsync(h->d_src, edge_src, nE * 4, cudaMemcpyHostToDevice, nullptr));
   CUDA_TRY(cudaMemcpyAsync(h->d_dst, edge_dst, nE * 4, cudaMemcpyHostToDevice, nullptr));
-  if (need_csr) {
-    CUDA_TRY(cudaMemcpyAsync(h->d_vptr, vptr.data(), (nV + 1) * 4, cudaMemcpyHostToDevice, nullptr));
-    CUDA_TRY(cudaMemcpyAsync(h->d_vidx, vidx.data(), 2 * nE * 4, cudaMemcpyHostToDevice, nullptr));
-  }
   CUDA_TRY(cudaMemcpyAsync(h->d_eoff, eoff.data(), (n_instances + 1) * 8, cudaMemcpyHostToDevice, nullptr));
   if (realloc_happened || h->hp == 0) {
     CUDA_TRY(cudaMemsetAsync(h->xV, 0, nV_pad * D * 4, nullptr));
     CUDA_TRY(cudaMemsetAsync(h->mV, 0, nV_pad * D * 4, nullptr));
+  }
+  // The host-side validation below runs while the (pinned-memory) uploads above are in flight.  A batch
+  // that fails it leaves the handle without a plan: the previous plan's buffers are already overwritten.
+  h->has_plan = false;
+  h->snap_T = -1;
+  // every edge row must connect two distinct vertices of its own instance: this is the
+  // block-diagonal structure of EV (instance_loader.py:56-66), checked like graphnn.check_run.
+  // CSR of EV^T (edge rows incident to every vertex): only the fp32 SIMT path segment-sums with it,
+  // the tensor-core path scatters from the edge side.
+  const bool need_csr = (h->hp == 0);
+  std::vector<int32_t> vptr(need_csr ? nV + 1 : 1, 0);
+  for (int k = 0; k < n_instances; ++k) {
+    // branch-free pass (unsigned range checks vectorise); the offending row is located only on failure
+    const uint32_t lo = static_cast<uint32_t>(voff[k]), span = static_cast<uint32_t>(voff[k + 1] - voff[k]);
+    uint32_t bad = 0;
+    for (int64_t e = eoff[k]; e < eoff[k + 1]; ++e) {
+      const uint32_t s = static_cast<uint32_t>(edge_src[e]) - lo, t = static_cast<uint32_t>(edge_dst[e]) - lo;
+      bad |= static_cast<uint32_t>(s >= span) | static_cast<uint32_t>(t >= span) | static_cast<uint32_t>(s == t);
+    }
+    if (bad)
+      for (int64_t e = eoff[k]; e < eoff[k + 1]; ++e) {
+        const int64_t s = edge_src[e], t = edge_dst[e];
+        if (s < voff[k] || s >= voff[k + 1] || t < voff[k] || t >= voff[k + 1] || s == t)
+        {
+          cudaStreamSynchronize(nullptr);
+          return fail(TSPGNN_E_INVALID,
+                      "Matrix EV: edge row %lld connects columns (%lld,%lld) outside instance %d's vertex range [%lld,%lld)",
+                      (long long)e, (long long)s, (long long)t, k, (long long)voff[k], (long long)voff[k + 1]);
+        }
+      }
+    if (need_csr)
+      for (int64_t e = eoff[k]; e < eoff[k + 1]; ++e) {
+        vptr[edge_src[e] + 1]++;
+        vptr[edge_dst[e] + 1]++;
+      }
+  }
+  std::vector<int32_t> vidx;
+  if (need_csr) {
+    for (int64_t v = 0; v < nV; ++v) vptr[v + 1] += vptr[v];
+    vidx.resize(2 * nE);
+    std::vector<int32_t> fill(vptr.begin(), vptr.end() - 1);
+    for (int64_t e = 0; e < nE; ++e) {
+      vidx[fill[edge_src[e]]++] = static_cast<int32_t>(e);
+      vidx[fill[edge_dst[e]]++] = static_cast<int32_t>(e);
+    }
+  }
+  if (need_csr) {
+    CUDA_TRY(cudaMemcpyAsync(h->d_vptr, vptr.data(), (nV + 1) * 4, cudaMemcpyHostToDevice, nullptr));
+    CUDA_TRY(cudaMemcpyAsync(h->d_vidx, vidx.data(), 2 * nE * 4, cudaMemcpyHostToDevice, nullptr));
   }
   if (h->hp > 0) {
     CUDA_TRY(cudaMemsetAsync(h->d_deg, 0, nV_pad * 4, nullptr));
