@@ -166,6 +166,8 @@ struct tspgnn_ctx {
   float *d_grads = nullptr, *d_adam_m = nullptr, *d_adam_v = nullptr, *d_scal = nullptr, *d_y = nullptr,
         *d_dvote = nullptr;
   int64_t cap_y = 0;
+  cudaStream_t side_stream = nullptr;     // vertex-side work of the reverse pass runs beside the edge-side kernels
+  cudaEvent_t ev_side[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t adam_step = 0;
   float lr = 2e-5f, l2 = 1e-10f, clip = 0.65f;                 // model.py:13-15
   float adam_b1 = 0.9f, adam_b2 = 0.999f, adam_eps = 1e-8f;    // tf.train.AdamOptimizer defaults
@@ -264,6 +266,9 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
   void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg};
   for (void* p : tp)
     if (p) cudaFree(p);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  for (cudaEvent_t e : h->ev_side)
+    if (e) cudaEventDestroy(e);
   if (g_const_owner == h) g_const_owner = nullptr;
   delete h;
   return 0;
