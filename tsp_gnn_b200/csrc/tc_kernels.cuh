@@ -63,6 +63,7 @@ struct K1Args {
   // of the incident edges), wV is the image of [W4.Kx ; Kh] and the V epilogue adds deg(v) * (b4.Kx),
   // c_vfold_bias, to z before the gate LayerNorms.  nullptr = unfolded.
   const float* vdeg;     // [sumV_pad] number of incident edges of every vertex row
+  const float* ln_tab;   // [2 cells][gamma'[5][64] | beta'[5][64]]: LayerNorm parameters as the epilogue wants them (see the prologue)
   long long* timeline;   // optional clock64() trace (tools/timeline.py), nullptr in production
 };
 
@@ -84,6 +85,7 @@ struct K2Args {
   // edge tiles run three layers, scatter the hidden activations a3, and the vertex cell applies
   // W4 (merged into its LSTM kernel) once per vertex instead of once per edge (K1Args::vdeg).
   int fold;
+  const float* bias_tab;   // [3 MLPs][4][64] biases (V_msg_E, E_msg_V, E_vote), coalesced copy for the prologue
   long long* timeline;
 };
 
@@ -604,16 +606,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
     // LayerNorm parameters of this CTA's cell.  The three gates that only feed a logistic function
     // (input 0, forget 2, output 3) are stored pre-multiplied by -log2(e), with the forget bias
     // folded into beta: the epilogue then gets the exponent of 2^(-x log2 e) straight from the FMA.
+    // (tspgnn_set_params builds that table once; a coalesced copy here instead of run-time indexed
+    // constant-bank reads, which serialise 32-way and sit on the critical path of the last SM to start)
     float* ln_sm = reinterpret_cast<float*>(smem + L::LN_OFF);
-    const CellLN& ln = c_ln[is_v ? 0 : 1];
-    constexpr float NL2E = -1.4426950408889634f;
-    for (int i = tid; i < 5 * D; i += TC_THREADS) {
-      const int g = i >> 6;
-      const bool sig = (g == 0) || (g == 2) || (g == 3);
-      const float gam = ln.gamma[g][i & 63], bet = ln.beta[g][i & 63] + (g == 2 ? FORGET_BIAS : 0.f);
-      ln_sm[i] = sig ? gam * NL2E : gam;
-      ln_sm[5 * D + i] = sig ? bet * NL2E : bet;
-    }
+    const float* tab = a.ln_tab + (is_v ? 0 : 2 * 5 * D);
+    for (int i = tid; i < 2 * 5 * D; i += TC_THREADS) ln_sm[i] = tab[i];
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -917,8 +914,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   if (warp == 12) ptx::tmem_alloc(tmem_slot, 256);
   {
     float* bias_sm = reinterpret_cast<float*>(smem + L::BIAS_OFF);
-    const MlpBias& bias = c_mlp_bias[a.vote_mode ? 2 : (is_v ? 0 : 1)];
-    for (int i = tid; i < 4 * D; i += K2_THREADS) bias_sm[i] = bias.b[i >> 6][i & 63];
+    const float* tab = a.bias_tab + (a.vote_mode ? 2 : (is_v ? 0 : 1)) * 4 * D;
+    for (int i = tid; i < 4 * D; i += K2_THREADS) bias_sm[i] = tab[i];
   }
   ptx::tcgen05_fence_before();
   __syncthreads();

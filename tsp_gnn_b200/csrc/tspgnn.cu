@@ -135,6 +135,8 @@ struct tspgnn_ctx {
   uint8_t* d_wlstm_vfold = nullptr;           // V cell with E_msg_V's output layer merged in: [W4.Kx ; Kh]
   float h_vfold_bias[4 * D];                  // (b4 . Kx), centred per gate
   float* d_deg = nullptr;                     // [sumV_pad] incident edges per vertex (folded path)
+  float* d_lntab = nullptr;                   // [2][640] LayerNorm tables of K1's prologue
+  float* d_biastab = nullptr;                 // [3][256] bias tables of K2's prologue
   bool fold = true;                           // tensor-core modes: inference timesteps use the folded output layer
   uint8_t* d_wmlp[3] = {nullptr, nullptr, nullptr};   // V_msg_E, E_msg_V, E_vote
   // plan
@@ -263,7 +265,7 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
     for (void* p : wp)
       if (p) cudaFree(p);
   }
-  void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg};
+  void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg, h->d_lntab, h->d_biastab};
   for (void* p : tp)
     if (p) cudaFree(p);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -335,6 +337,28 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
   // tensor-core operand images
   if (h->hp > 0) {
     const int hp = h->hp;
+    {
+      // LayerNorm parameters as K1's epilogue consumes them: the three gates that only feed a logistic
+      // function (input 0, forget 2, output 3) pre-multiplied by -log2(e), with the forget bias folded into
+      // beta, so that the exponent of 2^(-x log2 e) comes straight out of an FMA
+      constexpr float NL2E = -1.4426950408889634f;
+      std::vector<float> tab(2 * 2 * 5 * D), btab(3 * 4 * D);
+      for (int c = 0; c < 2; ++c)
+        for (int g = 0; g < 5; ++g)
+          for (int j = 0; j < D; ++j) {
+            const bool sig = (g == 0) || (g == 2) || (g == 3);
+            const float gam = h->h_ln[c].gamma[g][j], bet = h->h_ln[c].beta[g][j] + (g == 2 ? FORGET_BIAS : 0.f);
+            tab[(c * 2 + 0) * 5 * D + g * D + j] = sig ? gam * NL2E : gam;
+            tab[(c * 2 + 1) * 5 * D + g * D + j] = sig ? bet * NL2E : bet;
+          }
+      for (int m = 0; m < 3; ++m)
+        for (int l = 0; l < 4; ++l) memcpy(&btab[(m * 4 + l) * D], h->h_bias[m].b[l], D * 4);
+      if (!h->d_lntab && (dev_alloc(&h->d_lntab, static_cast<int64_t>(tab.size())) ||
+                          dev_alloc(&h->d_biastab, static_cast<int64_t>(btab.size()))))
+        return TSPGNN_E_CUDA;
+      CUDA_TRY(cudaMemcpy(h->d_lntab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(h->d_biastab, btab.data(), btab.size() * 4, cudaMemcpyHostToDevice));
+    }
     std::vector<uint8_t> img;
     std::vector<float> kc(2 * D * 4 * D);
     for (int c = 0; c < 2; ++c) {
@@ -621,6 +645,7 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, lon
   K2Args a;
   a.timeline = timeline;
   a.fold = (fold && !vote) ? 1 : 0;
+  a.bias_tab = h->d_biastab;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = vote ? h->d_wmlp[2] : h->d_wmlp[1];
@@ -651,6 +676,7 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, bool fold, long long* tim
   a.wE = h->d_wlstm[1];
   a.wV = fold ? h->d_wlstm_vfold : h->d_wlstm[0];
   a.vdeg = fold ? h->d_deg : nullptr;
+  a.ln_tab = h->d_lntab;
   a.mV = h->mV;
   a.xV = h->xV;
   a.src = h->d_src;
