@@ -300,6 +300,24 @@ def test_binary_search_cost_loop_runs_on_the_cached_plan():
         assert sess._engine.launch_count > 0
 
 
+def test_accuracy_sweep_over_sizes_and_deviations(tmp_path):
+    """experiments/test_varying_sizes.py / test_varying_dev.py loops through the Session surface: with a large
+    deviation the +-dev copies of an instance differ in C only, and accuracy is a mean over {0, 1} outcomes."""
+    from tsp_gnn_b200 import build_network, Session, global_variables_initializer, experiments, InstanceLoader
+    from tsp_gnn_b200.instances import create_dataset
+    loaders = {}
+    for n in (8, 12):
+        path = str(tmp_path / ("n=%d" % n))
+        create_dataset(path, n, n, samples=6, seed=n)
+        loaders[n] = InstanceLoader(path)
+    GNN = build_network(64)
+    with Session(GNN) as sess:
+        sess.run(global_variables_initializer(seed=2))
+        res = experiments.accuracy_sweep(sess, GNN, loaders, devs=[0.02, 0.1], time_steps=4, batch_size=3, n_batches=2)
+    assert sorted(res) == [(8, 0.02), (8, 0.1), (12, 0.02), (12, 0.1)]
+    assert all(0.0 <= v <= 1.0 for v in res.values())
+
+
 def test_example_drivers_train_save_and_evaluate(tmp_path):
     """examples/train.py + examples/test.py: the reference's train.py / test.py control flow (flags, run_batch,
     log.dat, checkpoint directory naming) end to end on a tiny generated dataset."""

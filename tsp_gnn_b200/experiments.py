@@ -4,6 +4,8 @@
 repeatedly evaluates ``predictions`` on the SAME graph.  ``Session.run`` recognises the unchanged
 incidence and skips ``tspgnn_plan``; every probe then costs E_init + the timestep loop + read-out.
 """
+from itertools import islice
+
 import numpy as np
 
 from .instances import create_batch
@@ -43,3 +45,26 @@ def get_cost(sess, model, instance, time_steps, threshold=0.5, stopping_delta=0.
         wpred = (wmax + wmin) / 2
         iterations += 1
     return wpred, pred, route_cost, iterations
+
+
+def get_accuracy(sess, model, batch, time_steps):
+    """experiments/test_varying_sizes.py:20-38 / test_varying_dev.py:20-38: ``acc`` of one batch."""
+    EV, W, C, route_exists, n_vertices, n_edges = batch
+    feed = {model["EV"]: EV, model["W"]: W, model["C"]: C, model["time_steps"]: time_steps,
+            model["route_exists"]: route_exists, model["n_vertices"]: n_vertices, model["n_edges"]: n_edges}
+    return float(np.mean(sess.run(model["acc"], feed_dict=feed)))
+
+
+def accuracy_sweep(sess, model, loaders, devs, time_steps, batch_size=16, n_batches=64):
+    """The sweeps behind figures/test_varying_sizes.png and test_varying_dev.png
+    (test_varying_sizes.py:82-113, test_varying_dev.py:81-96): mean accuracy over ``n_batches`` batches
+    for every (key, deviation).  ``loaders`` maps a key (e.g. the instance size n) to an InstanceLoader.
+    Returns {(key, dev): accuracy}; plotting and the result files stay with the caller."""
+    out = {}
+    for key, loader in loaders.items():
+        for dev in devs:
+            loader.reset()
+            accs = [get_accuracy(sess, model, batch, time_steps)
+                    for batch in islice(loader.get_batches(batch_size, dev), n_batches)]
+            out[(key, dev)] = float(np.mean(accs)) if accs else float("nan")
+    return out
