@@ -103,12 +103,28 @@ class ClockSampler(object):
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def make_workload(rank):
+def make_workload(rank=0):
+    """Config 2 as ONE rank would see it at N=1 (the CPU arms use this)."""
     from tsp_gnn_b200 import instances as inst
     from tsp_gnn_b200 import params as P
-    EV, W, C, y, nv, ne = inst.synth_batch([N_CITIES] * BATCH, seed=42 + 1000 * rank)
+    EV, W, C, y, nv, ne = inst.synth_batch([N_CITIES] * BATCH, seed=42)
     params = P.init_params(D, seed=0)
     return EV, W.astype(np.float32).reshape(-1), C.astype(np.float32).reshape(-1), y, nv, ne, params
+
+
+def shard_batch(sizes, seed, world, rank):
+    """Builds ONE global batch (identically on every rank: seeded) and cuts this rank's shard out of it with
+    the edge-count-balanced partitioner (instances are independent blocks of EV, instance_loader.py:56-66)."""
+    from tsp_gnn_b200 import instances as inst
+    from tsp_gnn_b200 import sharding
+    EV, W, C, y, nv, ne = inst.synth_batch(list(sizes), seed=seed)
+    parts = sharding.partition_instances(ne, world)
+    idx = parts[rank]
+    src, dst, Wl, Cl, nvl, nel = sharding.take_instances(idx, EV.src, EV.dst, W, C, nv, ne)
+    loads = [int(np.asarray(ne)[p].sum()) for p in parts]
+    return {"idx": idx, "src": src, "dst": dst, "W": Wl, "C": Cl, "nv": nvl, "ne": nel, "B": len(sizes),
+            "y": np.asarray(y, dtype=np.float32)[idx], "loads": loads, "nE": int(nel.sum()), "nV": int(nvl.sum()),
+            "nE_global": int(np.sum(ne)), "nV_global": int(np.sum(nv))}
 
 
 def cpu_loop_timesteps_per_s(params, EV, W, C, nv, ne, n_instances, timesteps, repeats):
@@ -136,7 +152,38 @@ def cpu_loop_timesteps_per_s(params, EV, W, C, nv, ne, n_instances, timesteps, r
     return timesteps / best, best, threads
 
 
+def cpu_arm(params, EV, W, C, nv, ne, timesteps, repeats, dense):
+    """One CPU arm on the full config-2 batch; returns the cpu_baseline-style dict."""
+    if dense:
+        v, sec, threads = cpu_loop_timesteps_per_s(params, EV, W, C, nv, ne, BATCH, timesteps, repeats)
+        what = "dense fp32 EV [99840,5120] multiplied like graphnn.py:156-160"
+    else:
+        from oracle import tspgnn_oracle as orc
+        from threadpoolctl import threadpool_info, threadpool_limits
+        nE, nV = int(np.sum(ne)), int(np.sum(nv))
+        P32 = {k: v.astype(np.float32) for k, v in params.items()}
+        src, dst = EV.src[:nE].astype(np.int64), EV.dst[:nE].astype(np.int64)
+        E_h = orc.mlp(np.stack([W[:nE], C[:nE]], axis=1).astype(np.float32), P32, "E_init_MLP")
+        V_h = np.tile(P32["V_init"] / np.sqrt(np.float32(D)), (nV, 1)).astype(np.float32)
+        E_c, V_c = np.zeros_like(E_h), np.zeros_like(V_h)
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        sec = float("inf")
+        with threadpool_limits(limits=ncpu):
+            for _ in range(repeats):
+                t0 = time.perf_counter()
+                orc.message_passing(P32, src, dst, None, E_c, E_h, V_c, V_h, timesteps)
+                sec = min(sec, time.perf_counter() - t0)
+            threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        v = timesteps / sec
+        what = "gather / np.add.at form of the same incidence products (no dense EV)"
+    return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "full batch 128 x n=40, %s, %d timesteps, best of %d (%.1f s each)" % (what, timesteps, repeats, sec)}
+
+
 def run_reference(args):
+    """CPU arm: the reference's algorithm for the path on this box's host cores.  The reference's own files
+    (graphnn.py on the TF1 stand-in of oracle/tf1_shim.py) run only where /root/reference exists, which is
+    not the GPU box, so this arm times the oracle's restatement of the same dense-EV loop (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -151,15 +198,144 @@ def run_reference(args):
         t_total += sec
     value = ts * steps / t_total
     sample = "full batch 128 x n=40, dense fp32 EV [99840,5120], %d timesteps per step, %d steps" % (ts, steps)
+    sparse = cpu_arm(params, EV, W, C, nv, ne, 2, 1, dense=False)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": 1, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "timesteps_per_step": ts, "note": "oracle port of the reference's "
-                       "dense-EV TensorFlow CPU loop (TensorFlow 1.x is not installable here); numpy/BLAS threads"},
+                       "dense-EV TensorFlow CPU loop (TensorFlow 1.x is not installable here and /root/reference "
+                       "does not travel to the GPU box); numpy/BLAS threads"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline_sparse": sparse,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+class ShardRunner(object):
+    """One rank's shard of a global batch on one Engine: the device-resident hot step and the end-to-end
+    step, both ending in the ONE collective of the path (all-reduce of the zero-padded logits vector)."""
+
+    def __init__(self, eng, shard, world, dev, torch, dist):
+        self.eng, self.sh, self.world, self.dev, self.torch, self.dist = eng, shard, world, dev, torch, dist
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        self.hW, self.hC = pin(shard["W"]), pin(shard["C"])
+        self.hsrc, self.hdst = pin(shard["src"]).numpy(), pin(shard["dst"]).numpy()
+        self.B_local = int(len(shard["idx"]))
+        self.dW = torch.empty(shard["nE"], dtype=torch.float32, device=dev)
+        self.dC = torch.empty(shard["nE"], dtype=torch.float32, device=dev)
+        self.d_logits = torch.empty(self.B_local, dtype=torch.float32, device=dev)
+        self.d_preds = torch.empty(self.B_local, dtype=torch.float32, device=dev)
+        self.d_full = torch.zeros(shard["B"], dtype=torch.float32, device=dev)
+        self.d_idx = torch.from_numpy(np.asarray(shard["idx"], dtype=np.int64)).to(dev)
+        self.h_full = torch.empty(shard["B"], dtype=torch.float32).pin_memory()
+        eng.plan(shard["nv"], shard["ne"], self.hsrc, self.hdst)
+
+    def collective(self):
+        """All-reduce of the zero-padded global logits vector on the engine's stream (the caller holds it)."""
+        self.d_full.zero_()
+        self.d_full.index_copy_(0, self.d_idx, self.d_logits)
+        if self.world > 1:
+            self.dist.all_reduce(self.d_full)
+
+    def hot_step(self):
+        """Timed unit of `value`: 32 timesteps on the resident state, vote read-out, the collective."""
+        self.eng.step(T_STEPS)
+        self.eng.readout(self.d_logits, self.d_preds)
+        self.collective()
+
+    def init_state(self):
+        self.dW.copy_(self.hW, non_blocking=True)
+        self.dC.copy_(self.hC, non_blocking=True)
+        self.eng.init_embeddings(self.dW, self.dC)
+
+    def e2e_step(self):
+        """What a user of the reference's sess.run gets: host buffers in, global logits on the host out."""
+        eng, sh = self.eng, self.sh
+        eng.plan(sh["nv"], sh["ne"], self.hsrc, self.hdst)
+        if self.world == 1:
+            logits, preds = eng.forward_host(self.hW.numpy(), self.hC.numpy(), T_STEPS)
+            return logits
+        stream = eng.stream()
+        with self.torch.cuda.stream(stream):
+            self.dW.copy_(self.hW, non_blocking=True)
+            self.dC.copy_(self.hC, non_blocking=True)
+            eng.forward_device(self.dW, self.dC, T_STEPS, self.d_logits, self.d_preds)
+            self.collective()
+            self.h_full.copy_(self.d_full, non_blocking=True)
+        stream.synchronize()
+        return self.h_full.numpy()
+
+    def h2d_bytes(self, mode):
+        sh = self.sh
+        return int(2 * sh["nE"] * 4 + 2 * sh["nE"] * 4 + (self.B_local + 1) * 8
+                   + ((2 * sh["nE"] * 4 + (sh["nV"] + 1) * 4) if mode == "simt" else 0))
+
+
+def timed_legs(run, args, steps, warmup, flush, barrier, world, torch, dist, dev, sampler_index=None):
+    """Device-resident leg (CUDA events on the engine's stream, L2 flushed between steps, max over ranks) and
+    end-to-end leg (host clock around barrier + synchronize, max over ranks) of one ShardRunner."""
+    eng, stream = run.eng, run.eng.stream()
+    with torch.cuda.stream(stream):
+        run.init_state()
+        for _ in range(warmup):
+            run.hot_step()
+    stream.synchronize()
+    sampler = None
+    if sampler_index is not None:
+        sampler = ClockSampler(sampler_index)
+        sampler.start()
+        sampler.wait_first_sample()
+    barrier()
+    t_clock0 = time.time()
+    launches0 = eng.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.fill_(1)                 # evict the recurrent state from L2 (not timed)
+            a.record(stream)
+            run.hot_step()
+            b.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = eng.launch_count - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop(t_clock0, time.time()) if sampler is not None else None
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    # the collective alone (device time per call, this rank)
+    coll_us = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            for _ in range(5):
+                run.collective()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(50):
+                run.collective()
+            b.record(stream)
+        stream.synchronize()
+        coll_us = 1e3 * a.elapsed_time(b) / 50
+    # end-to-end
+    out = None
+    for _ in range(max(1, min(warmup, 3))):
+        out = run.e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = run.e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    assert np.all(np.isfinite(out))
+    return {"dev_ms": dev_ms, "t_wall": t_wall, "launches": int(launches), "clocks": clocks, "coll_us": coll_us,
+            "e2e_s": e2e_s, "logits": np.array(out, copy=True)}
 
 
 def run_ours(args):
@@ -175,17 +351,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from tsp_gnn_b200.engine import Engine
-    from tsp_gnn_b200 import sharding
+    from tsp_gnn_b200 import params as P
 
-    EV, W, C, y, nv, ne, params = make_workload(rank)
-    nE, nV = int(ne.sum()), int(nv.sum())
+    params = P.init_params(D, seed=0)
+    # ONE global batch of 128 instances per GPU (per-GPU work fixed = config 2), instance-sharded
+    shard = shard_batch([N_CITIES] * (BATCH * world), 42, world, rank)
+    nE, nV = shard["nE"], shard["nV"]
     eng = Engine(D, args.mode, local)
     eng.set_params(params)
-    eng.plan(nv, ne, EV.src, EV.dst)
+    if args.legacy_kernels:
+        eng.set_option("fused", 0)
+    run = ShardRunner(eng, shard, world, dev, torch, dist)
     stream = eng.stream()
-    dW, dC = torch.from_numpy(W).to(dev), torch.from_numpy(C).to(dev)
-    d_logits = torch.empty(BATCH, dtype=torch.float32, device=dev)
-    d_preds = torch.empty(BATCH, dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def barrier():
@@ -193,102 +370,81 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident leg: `value` --------------------------------
-    with torch.cuda.stream(stream):
-        eng.init_embeddings(dW, dC)
-        for _ in range(args.warmup):
-            eng.step(T_STEPS)
-    stream.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
-    sampler.wait_first_sample()
-    barrier()
-    t_clock0 = time.time()
-    launches0 = eng.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    with torch.cuda.stream(stream):
-        for a, b in ev:
-            flush.fill_(1)                 # evict the recurrent state from L2 (not timed)
-            a.record(stream)
-            eng.step(T_STEPS)
-            b.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = eng.launch_count - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop(t_clock0, time.time())
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    legs = timed_legs(run, args, args.steps, args.warmup, flush, barrier, world, torch, dist, dev, sampler_index=local)
+    dev_ms = legs["dev_ms"]
     value = world * T_STEPS * args.steps / (dev_ms * 1e-3)
+    e2e = {"value": world * T_STEPS * args.steps / legs["e2e_s"], "unit": UNIT,
+           "h2d_bytes_per_step": run.h2d_bytes(args.mode),
+           "d2h_bytes_per_step": int(2 * run.B_local * 4 if world == 1 else shard["B"] * 4),
+           "ms_per_step": 1e3 * legs["e2e_s"] / args.steps,
+           "includes": "tspgnn_plan (incidence upload) + H2D of W, C + E_init + 32 timesteps + vote read-out + "
+                       + ("D2H (tspgnn_forward_host)" if world == 1 else
+                          "all-reduce of the zero-padded global logits on the engine's stream + one D2H")}
 
     # ---------------- per-kernel roofline ---------------------------------------------
     roof = None
     if args.mode != "simt":
+        fused = not args.legacy_kernels
         with torch.cuda.stream(stream):
-            k1_ms = eng.time_kernel(0, 20)
+            run.init_state()
+            eng.step(4)
+            k1_ms = eng.time_kernel(2 if fused else 0, 20)
             k2_ms = eng.time_kernel(1, 20)
+        stream.synchronize()
         total_b, k1_b = algorithmic_bytes(nE, nV, 4)
+        kern_b = total_b if fused else k1_b
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        ach = k1_b / (k1_ms * 1e-3) / 1e9
+        ach = kern_b / (k1_ms * 1e-3) / 1e9
+        kname = ("tc_step_kernel<%d>" if fused else "tc_lnlstm_kernel<%d>") % (2 if args.mode == "bf16x3" else 1)
         traffic = None        # DRAM bytes per launch of this kernel from the committed ncu --set full capture
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "tc_lnlstm_kernel<%d>" % (2 if args.mode == "bf16x3" else 1))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kname)
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "tc_lnlstm_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+        step_frac = (total_b / (peak * 1e9)) / (dev_ms * 1e-3 / (T_STEPS * args.steps))
+        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
-                "algorithmic_bytes_per_launch": k1_b, "kernel_ms": k1_ms, "mlp_kernel_ms": k2_ms,
+                "algorithmic_bytes_per_launch": kern_b, "kernel_ms": k1_ms, "mlp_kernel_ms": k2_ms,
+                "what": ("one launch of the fused timestep kernel = one whole timestep (cells + messages of the new "
+                         "state): SURVEY 8(d)'s bytes per timestep" if fused else
+                         "the LayerNorm-LSTM kernel of the two-kernel sequence"),
                 "timing": "CUDA events around single launches on the engine's stream, 20 launches each, right after "
-                          "the timed region (tspgnn_time_kernel); inside the graph the two kernels cannot be bracketed",
-                "step_frac_of_hbm_floor": (total_b / (peak * 1e9)) / (dev_ms * 1e-3 / (T_STEPS * args.steps))}
+                          "the timed region (tspgnn_time_kernel)",
+                "step_frac": step_frac,
+                "step_frac_what": "algorithmic bytes of a timestep / measured HBM peak / measured time per timestep of "
+                                  "the timed region (incl. read-out and collective)"}
 
-    # ---------------- end-to-end leg through the host-buffer C-ABI call -----------------
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    hW, hC, hsrc, hdst = pin(W), pin(C), pin(EV.src), pin(EV.dst)
-    idx = np.arange(BATCH)
-    def e2e_step():
-        eng.plan(nv, ne, hsrc, hdst)
-        logits, preds = eng.forward_host(hW, hC, T_STEPS)
-        if world > 1:      # instance-sharded batch: one all-reduce of the zero-padded logits
-            full = torch.zeros(world * BATCH, dtype=torch.float32, device=dev)
-            full[rank * BATCH:(rank + 1) * BATCH] = torch.from_numpy(logits).to(dev)
-            dist.all_reduce(full)
-            return full.cpu().numpy()
-        return logits
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e = {"value": world * T_STEPS * args.steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(hW.nbytes + hC.nbytes + hsrc.nbytes + hdst.nbytes + (BATCH + 1) * 8
-                                     + ((2 * nE * 4 + (nV + 1) * 4) if args.mode == "simt" else 0)),
-           "d2h_bytes_per_step": int(2 * BATCH * 4), "ms_per_step": 1e3 * e2e_s / args.steps,
-           "includes": "tspgnn_plan (incidence upload) + E_init + 32 timesteps + vote read-out + D2H"}
-    assert np.all(np.isfinite(out))
+    # ---------------- config 4: ONE batch of 512 mixed instances, strong scaling over the ranks -------------
+    cfg4 = None
+    if not args.no_config4:
+        from tsp_gnn_b200 import instances as inst
+        sh4 = shard_batch(inst.mixed_sizes(512, 20, 60, seed=42), 42, world, rank)
+        run4 = ShardRunner(eng, sh4, world, dev, torch, dist)
+        st4 = max(3, min(args.steps, 20))
+        l4 = timed_legs(run4, args, st4, 3, flush, barrier, world, torch, dist, dev)
+        loads = sh4["loads"]
+        cfg4 = {"workload": "config4: ONE batch of 512 instances, n uniform in 20..60 (seed 42), %d edge rows, "
+                            "instance-sharded over %d rank(s) by sharding.partition_instances" % (sh4["nE_global"], world),
+                "scaling": "strong",
+                "timesteps_per_s": T_STEPS * st4 / (l4["dev_ms"] * 1e-3),
+                "instances_per_s_e2e": 512 * st4 / l4["e2e_s"],
+                "ms_per_step": l4["dev_ms"] / st4, "e2e_ms_per_step": 1e3 * l4["e2e_s"] / st4,
+                "edge_rows_per_rank": loads, "imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads)),
+                "collective_us": l4["coll_us"], "steps": st4}
+        run = ShardRunner(eng, shard, world, dev, torch, dist)      # back to the headline plan
 
     # ---------------- training step (secondary) ---------------------------------
     train = None
     if args.train_steps > 0:
-        yf = np.asarray(y, dtype=np.float32)
+        yf = shard["y"]
         eng.set_hyper()                                  # model.py:13-15 defaults
-        eng.plan(nv, ne, hsrc, hdst)
+        eng.plan(shard["nv"], shard["ne"], run.hsrc, run.hdst)
+        hW, hC = run.hW.numpy(), run.hC.numpy()
         eng.train_step_host(hW, hC, yf, T_STEPS)         # warm-up (allocates snapshots / scratch)
         barrier()
         t0 = time.perf_counter()
@@ -298,31 +454,41 @@ def run_ours(args):
         tr_s = (time.perf_counter() - t0) / args.train_steps
         train = {"ms_per_step": 1e3 * tr_s, "instances_per_s": world * BATCH / tr_s, "loss": tr_loss,
                  "what": "tspgnn_train_step_host: H2D, training forward (32 timesteps, snapshots), reverse pass, "
-                         "L2 + clip + Adam, operand refresh, D2H (model.py:157-167); per-GPU batch, no gradient "
+                         "L2 + clip + Adam, operand refresh, D2H (model.py:157-167); per-GPU shard, no gradient "
                          "all-reduce in this leg"}
         eng.set_params(params)                           # the legs below use the seeded variables again
 
-    # ---------------- CPU baseline beside it (rank 0, N=1) ---------------------------------
-    cpu = None
+    # ---------------- CPU baselines beside it (rank 0, N=1) ---------------------------------
+    cpu = cpu_sparse = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, threads = cpu_loop_timesteps_per_s(params, EV, W, C, nv, ne, BATCH, 2, 2)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "full batch 128 x n=40 with the dense fp32 EV [99840,5120] like graphnn.py:156-160, "
-                         "2 timesteps, best of 2 (%.1f s each)" % sec}
+        EV, W, C, y, nv, ne, _ = make_workload(0)
+        cpu = cpu_arm(params, EV, W, C, nv, ne, 2, 2, dense=True)
+        cpu_sparse = cpu_arm(params, EV, W, C, nv, ne, 2, 2, dense=False)
 
     if rank == 0:
+        loads = shard["loads"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": {"bf16x3": "f32 (tcgen05 bf16 hi/lo split operands x3, fp32 accumulate, fp32 state)",
-                          "bf16": "bf16 operands / fp32 accumulate, fp32 c state", "simt": "f32"}[args.mode],
+                "dtype": {"bf16x3": "f32 (tcgen05 kind::f16 on bf16 hi+lo split operands, 3 MMAs per product, fp32 "
+                                    "accumulate; h stored as bf16 hi+lo = 16 mantissa bits, c fp32)",
+                          "bf16": "bf16 operands / fp32 accumulate, h stored bf16, c fp32", "simt": "f32"}[args.mode],
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "mode": args.mode,
-                           "timesteps_per_step": T_STEPS, "l2": "flushed between steps (256 MiB fill); within a "
-                           "step the 53.7 MB recurrent state is re-used across the 32 timesteps",
-                           "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "train_step": train}
+                "config": {"workload": WORKLOAD + "; ONE global batch of %d instances built on every rank and "
+                           "instance-sharded by sharding.partition_instances (edge-count LPT), %d per GPU"
+                           % (shard["B"], run.B_local),
+                           "per_gpu_batch": run.B_local, "global_batch": shard["B"], "mode": args.mode,
+                           "kernels": "two-kernel sequence (K2, K1)" if args.legacy_kernels else "fused CTA-pair timestep kernel",
+                           "timesteps_per_step": T_STEPS,
+                           "timed_region": "32 timesteps on the resident state + vote read-out + all-reduce of the "
+                                           "zero-padded global logits (NCCL, issued on the engine's stream; absent at N=1)",
+                           "edge_rows_per_rank": loads, "imbalance_max_over_mean": max(loads) / (sum(loads) / len(loads)),
+                           "collective_us": legs["coll_us"],
+                           "l2": "flushed between steps (256 MiB fill); within a step the 53.7 MB recurrent state "
+                                 "is re-used across the 32 timesteps",
+                           "wall_ms_per_step_incl_flush": 1e3 * legs["t_wall"] / args.steps},
+                "e2e": e2e, "gpu_launches": legs["launches"], "clocks": legs["clocks"], "roofline": roof,
+                "cpu_baseline": cpu, "cpu_baseline_sparse": cpu_sparse, "config4": cfg4, "train_step": train}
         print(json.dumps(line))
     eng.close()
     if world > 1:
@@ -337,6 +503,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bf16x3", choices=["bf16x3", "bf16", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 (512 mixed instances, strong scaling) block")
+    ap.add_argument("--legacy-kernels", action="store_true", help="two-kernel timestep (K2, K1) instead of the fused kernel")
     ap.add_argument("--train-steps", type=int, default=3, help="training steps timed for the secondary train_step block (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

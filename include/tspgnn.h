@@ -53,6 +53,12 @@ int tspgnn_create(int d, int mode, int device, tspgnn_handle* out);
 int tspgnn_destroy(tspgnn_handle h);
 int tspgnn_get_mode(tspgnn_handle h);
 
+/* Tuning / diagnosis knobs (no equivalent in the reference).  "fused" (default 1): tspgnn_step runs one
+ * fused CTA-pair kernel per timestep (tensor-core modes); 0 selects the two-kernel sequence (message MLPs,
+ * then LSTM cells), which computes the same thing.  "v_pair_weight": relative cost of a vertex tile pair
+ * used to split the clusters of the fused kernel between edge and vertex tiles. */
+int tspgnn_set_option(tspgnn_handle h, const char* name, double value);
+
 /* Replaces tf.global_variables_initializer() / Saver.restore (train.py:210, util.py:17):
  * uploads the flat fp32 blob (host pointer) and prepares the on-device operand images. */
 int tspgnn_set_params(tspgnn_handle h, const float* host_blob, int64_t n_floats);
@@ -142,10 +148,10 @@ int64_t tspgnn_launch_count(tspgnn_handle h);
 /* Measurement hook for bench.py's roofline line: launches ONE kernel of the timestep
  * `iters` times on `stream`, each launch bracketed by CUDA events, and returns the mean
  * duration in milliseconds.  which: 0 = LayerNorm-LSTM kernel (K1), 1 = message-MLP kernel
- * (K2).  Tensor-core modes only.  The recurrent state keeps evolving while this runs. */
+ * (K2), 2 = the fused timestep kernel (cells + messages of the new state, what tspgnn_step launches).  Tensor-core modes only.  The recurrent state keeps evolving while this runs. */
 int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* mean_ms, void* stream);
 
-/* Development aid: one launch of K1 (which = 0) or K2 (which = 1) with a clock64() trace of the
+/* Development aid: one launch of K1 (which = 0), K2 (which = 1) or the fused kernel (which = 2) with a clock64() trace of the
  * warp roles, copied to out_host[cta][role][tile][event] (148*4*64*8 int64). */
 int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_host, int64_t n_int64, void* stream);
 

@@ -100,6 +100,18 @@ def init_params(d=D_DEFAULT, seed=0, perturb_ln=False):
 # ----------------------------------------------------------------------------
 # building blocks
 # ----------------------------------------------------------------------------
+def spread_params(params, kernel_scale, logit_shift):
+    """Test parameter set whose predictions spread over (0, 1): with the reference initialisers every
+    prediction of a batch sits within ~1e-4 of the others, so a kernel that ignored most of the graph would
+    still pass a 1e-4 gate.  Scaling every kernel makes the network less contractive (instances end in
+    visibly different states) and the shift of the last vote bias centres the logits around zero."""
+    out = {}
+    for k, v in params.items():
+        out[k] = (v * np.float32(kernel_scale)).astype(np.float32) if k.endswith("kernel") else v.copy()
+    out["E_vote_MLP_layer_4/bias"] = (out["E_vote_MLP_layer_4/bias"] - np.float32(logit_shift)).astype(np.float32)
+    return out
+
+
 def sigmoid(x):
     """Stable logistic; same value as 1/(1+exp(-x)) wherever that does not overflow."""
     e = np.exp(-np.abs(x))

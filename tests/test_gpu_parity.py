@@ -69,6 +69,51 @@ def test_forward_matches_oracle_and_golden(mode, name):
     assert state_err(got["E_c"][:32], GOLD[name + "/E_c_head"]) <= TOL_STATE[mode]
 
 
+# Discriminating parity case: predictions spread over (0.15, 0.85) (with the reference initialisers all 16
+# predictions agree to four digits, so a 1e-4 gate on them alone says little).  The scaled kernels also make
+# the loop less contractive: the fp32 dense oracle itself moves 1.4e-6 (x2.5) / 1.1e-5 (x3) away from float64.
+TOL_SPREAD_PRED = {"spread25_16x20": {"simt": 2e-5, "bf16x3": 1e-4, "bf16": 5e-2},
+                   "spread30_16x20": {"simt": 1e-4, "bf16x3": 1e-4, "bf16": 1e-1}}
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", sorted(make_golden.SPREAD_CASES))
+def test_spread_predictions_match_oracle_and_golden(mode, name):
+    EV, W, C, y, nv, ne, params, T = make_golden.spread_case_inputs(name)
+    got = run_engine(mode, params, EV, W, C, nv, ne, T)
+    ref = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, T, dtype=np.float64)
+    assert ref["predictions"].max() - ref["predictions"].min() > 0.3      # the case really spreads
+    errp = float(np.abs(got["predictions"] - ref["predictions"]).max())
+    err = {k: state_err(got[k], ref[k]) for k in ("E_h", "E_c", "V_h", "V_c")}
+    print(mode, name, "pred err", errp, err)
+    assert errp <= TOL_SPREAD_PRED[name][mode], errp
+    assert np.abs(got["predictions"] - GOLD[name + "/predictions"]).max() <= TOL_SPREAD_PRED[name][mode]
+    if mode != "bf16":
+        for k in ("E_h", "E_c", "V_h", "V_c"):
+            assert err[k] <= 10 * TOL_STATE[mode], (k, err)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_fused_and_two_kernel_timesteps_agree(mode):
+    """tspgnn_step's fused CTA-pair kernel against the two-kernel sequence (K2, K1) it replaces: same
+    arithmetic, different routing (h' stays on chip, one launch per timestep)."""
+    sizes = inst.mixed_sizes(24, 10, 40, seed=3)
+    EV, W, C, y, nv, ne = inst.synth_batch(sizes, seed=17)
+    params = orc.init_params(64, seed=5, perturb_ln=True)
+    outs = []
+    for fused in (1, 0):
+        eng = make_engine(mode, params)
+        eng.set_option("fused", fused)
+        eng.plan(nv, ne, EV.src, EV.dst)
+        logits, preds = eng.forward_host(W, C, 7)
+        st = eng.get_states()
+        outs.append((preds, st["E"][1].cpu().numpy(), st["V"][1].cpu().numpy(), st["E"][0].cpu().numpy()))
+        eng.close()
+    tol = 2e-5 if mode == "bf16x3" else 2e-2      # fp32 re-association of the scatter order only
+    for a, b in zip(outs[0], outs[1]):
+        assert np.abs(a - b).max() <= tol, np.abs(a - b).max()
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_single_timestep_from_random_state(mode):
     """One while_body iteration (graphnn.py:142-173) from arbitrary (c,h): isolates the step kernels."""

@@ -13,7 +13,12 @@ eng.set_params(P.init_params(64, seed=0))
 eng.plan(nv, ne, EV.src, EV.dst)
 dW = torch.from_numpy(W.astype(np.float32).reshape(-1)).cuda(); dC = torch.from_numpy(C.astype(np.float32).reshape(-1)).cuda()
 eng.init_embeddings(dW, dC); eng.step(4); eng.stream().synchronize()
-for which, name, roles in ((0, "K1 lnlstm", ["epiWG0", "epiWG1", "mma", "producer"]), (1, "K2 mlp", ["chainWG0", "chainWG1", "mma", "-"])):
+which_sel = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2]
+ctas_sel = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 70, 147]
+for which, name, roles in ((0, "K1 lnlstm", ["epiWG0", "epiWG1", "mma", "producer"]), (1, "K2 mlp", ["chainWG0", "chainWG1", "mma", "-"]),
+                           (2, "fused step", ["chainWG0", "chainWG1", "mma/relay", "producer"])):
+    if which not in which_sel:
+        continue
     buf = np.zeros(148 * 4 * 64 * 8, dtype=np.int64)
     _lib.check(_lib.lib.tspgnn_debug_timeline(eng._h, which, buf.ctypes.data_as(ctypes.c_void_p), buf.size, eng._sptr()))
     tl = buf.reshape(148, 4, 64, 8)
@@ -27,7 +32,7 @@ for which, name, roles in ((0, "K1 lnlstm", ["epiWG0", "epiWG1", "mma", "produce
     spans.sort(reverse=True)
     print("==", name, "per-CTA (span cycles, cta, tiles): slowest 10 / fastest 4; mean span %.0f" % np.mean([x[0] for x in spans]))
     print("   ", spans[:10], "...", spans[-4:])
-    for cta in (0, 70, 147):
+    for cta in ctas_sel:
         t = tl[cta]
         base = t[t > 0].min() if (t > 0).any() else 0
         print("==", name, "cta", cta, "span", int(t.max() - base))

@@ -26,6 +26,7 @@ SIGNATURES = [
     ("tspgnn_create", ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     ("tspgnn_destroy", ctypes.c_int, [ctypes.c_void_p]),
     ("tspgnn_get_mode", ctypes.c_int, [ctypes.c_void_p]),
+    ("tspgnn_set_option", ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_double]),
     ("tspgnn_set_params", ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]),
     ("tspgnn_plan", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_void_p]),

@@ -176,7 +176,10 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
 // until the first accumulator is ready and have the registers to keep every load in flight: the
 // first gather drops from three L2 round trips to one and the gather warps start on tile 1 at once.
 template <int HP, bool IS_V>
-__device__ __forceinline__ void k1_boot_fill(const K1Args& a, uint8_t* slot, int warp, int lane, int tile) {
+__device__ __forceinline__ void k1_boot_fill_tile(const float* __restrict__ mV, float* __restrict__ xV,
+                                                  const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                                  uint8_t* slot, int warp, int lane, int tile) {
+  struct { const float* mV; float* xV; const int32_t* src; const int32_t* dst; } a = {mV, xV, src, dst};
   const int r8 = lane & 7, cq = lane >> 3;
   const uint32_t slot_s = ptx::smem_u32(slot);
   const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
@@ -216,6 +219,11 @@ __device__ __forceinline__ void k1_boot_fill(const K1Args& a, uint8_t* slot, int
       if (HP == 2) ptx::sts128(off + PLANE_BYTES, lo);
     }
   }
+}
+
+template <int HP, bool IS_V>
+__device__ __forceinline__ void k1_boot_fill(const K1Args& a, uint8_t* slot, int warp, int lane, int tile) {
+  k1_boot_fill_tile<HP, IS_V>(a.mV, a.xV, a.src, a.dst, slot, warp, lane, tile);
 }
 
 template <int HP, bool IS_V>
@@ -399,20 +407,21 @@ __device__ __forceinline__ float2 one_plus_ex2(float2 t) {
   return __fadd2_rn(make_float2(ptx::ex2_approx(t.x), ptx::ex2_approx(t.y)), make_float2(1.0f, 1.0f));
 }
 
-template <int HP, int CELL, bool CLAMP>
-__device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
-                                            uint64_t* acc_empty, int warp, int lane, long long* tl_, uint32_t ln_s,
-                                            const float* __restrict__ vdeg) {
-  // ln_s: shared-memory copy of this cell's LayerNorm parameters, gamma[g][j] at ln_s + (g*64+j)*4,
-  // beta at +1280.  (Run-time indexed constant-bank loads cost ~10 cycles each; a broadcast
-  // LDS.128 brings four values in ~2.)
-  const int e = warp >> 2, q4 = warp & 3;
-  long long* tl = (q4 == 0 && lane == 0) ? tl_ : nullptr;
-  const int r = q4 * 32 + lane;
-  const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 256;
-  int use = 0;
-  for (int n = e; n < ntiles; n += 2, ++use) {
-    uint8_t* gtile = state + static_cast<int64_t>(t0 + n) * tile_bytes(HP);
+// One tile of the LayerNorm-LSTM epilogue for the thread that owns row r (TMEM lane r).
+// FUSED = false: the stand-alone cell kernel (K1) - the accumulator goes back to the MMA warp with the
+//                last TMEM read.
+// FUSED = true : the fused timestep kernel (tc_fused.cuh) - the new h planes are ALSO stored into the
+//                tile's shared-memory slot `hslot_s` as the A operand of the message MLP, and the
+//                accumulator is kept (the MLP layers reuse its columns).
+// ln_s: shared-memory copy of this cell's LayerNorm parameters, gamma[g][j] at ln_s + (g*64+j)*4,
+// beta at +1280.  (Run-time indexed constant-bank loads cost ~10 cycles each; a broadcast
+// LDS.128 brings four values in ~2.)
+template <int HP, int CELL, bool CLAMP, bool FUSED>
+__device__ __forceinline__ void k1_cell_tile(uint8_t* gtile, int r, int lane, uint32_t t_acc, uint64_t* acc_full_bar,
+                                             uint32_t acc_parity, uint64_t* acc_empty_bar, uint32_t ln_s,
+                                             const float* __restrict__ vdeg_row, uint32_t hslot_s, long long* tl, int e,
+                                             int n) {
+  {
     float4* cg = reinterpret_cast<float4*>(gtile + HP * PLANE_BYTES) + r;   // chunk q at cg[q * 128]
     uint4* hg = reinterpret_cast<uint4*>(gtile) + r;                        // plane p, chunk ch at hg[p*1024 + ch*128]
     // first 32 columns of the old cell state: issued before the accumulator is ready
@@ -423,14 +432,14 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
       nx1[q] = cg[(4 + q) * 128];
     }
     tl_mark(tl, e, n, 0);
-    ptx::mbar_wait(&acc_full[e], use & 1);
+    ptx::mbar_wait(acc_full_bar, acc_parity);
     tl_mark(tl, e, n, 1);
     ptx::tcgen05_fence_after();
 
-    if (CELL == 0 && vdeg != nullptr) {
+    if (CELL == 0 && vdeg_row != nullptr) {
       // folded E_msg_V output layer: z += deg(v) * (b4 . Kx)   (vertex tiles only, 5 % of the rows).
       // Fully unrolled so that the bias values are constant-bank operands of the FMAs.
-      const float dg = vdeg[static_cast<int64_t>(t0 + n) * TILE_ROWS + r];
+      const float dg = *vdeg_row;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float zz[64];
@@ -518,10 +527,10 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
     for (int cc = 0; cc < 4; ++cc) {
       float vo[16], cs[16];
       ptx::tmem_ld16x2(t_acc + 3 * 64 + cc * 16, t_acc + cc * 16, vo, cs);
-      if (cc == 3) {     // last TMEM read of this tile: hand the accumulator back to the MMA warp
+      if (!FUSED && cc == 3) {     // last TMEM read of this tile: hand the accumulator back to the MMA warp
         ptx::tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[e]);
+        if (lane == 0) ptx::mbar_arrive(acc_empty_bar);
       }
       const uint32_t lcc = ln_s + cc * 64;
       float2 c2[8];
@@ -552,11 +561,35 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
         cg[(cc * 4 + q) * 128] = make_float4(c2[2 * q].x, c2[2 * q].y, c2[2 * q + 1].x, c2[2 * q + 1].y);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {   // two 16-B chunks of 8 bf16
-        hg[(cc * 2 + q) * 128] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-        if (HP == 2) hg[1024 + (cc * 2 + q) * 128] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        const uint4 h4 = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        const uint4 l4 = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        hg[(cc * 2 + q) * 128] = h4;
+        if (HP == 2) hg[1024 + (cc * 2 + q) * 128] = l4;
+        if (FUSED) {     // same chunk-major image in shared memory: A operand of the first MLP layer
+          const uint32_t so = hslot_s + (cc * 2 + q) * 2048 + r * 16;
+          ptx::sts128(so, h4);
+          if (HP == 2) ptx::sts128(so + PLANE_BYTES, l4);
+        }
       }
     }
     tl_mark(tl, e, n, 5);
+  }
+}
+
+template <int HP, int CELL, bool CLAMP>
+__device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
+                                            uint64_t* acc_empty, int warp, int lane, long long* tl_, uint32_t ln_s,
+                                            const float* __restrict__ vdeg) {
+  const int e = warp >> 2, q4 = warp & 3;
+  long long* tl = (q4 == 0 && lane == 0) ? tl_ : nullptr;
+  const int r = q4 * 32 + lane;
+  const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 256;
+  int use = 0;
+  for (int n = e; n < ntiles; n += 2, ++use) {
+    uint8_t* gtile = state + static_cast<int64_t>(t0 + n) * tile_bytes(HP);
+    const float* vdeg_row = (vdeg != nullptr) ? vdeg + static_cast<int64_t>(t0 + n) * TILE_ROWS + r : nullptr;
+    k1_cell_tile<HP, CELL, CLAMP, false>(gtile, r, lane, t_acc, &acc_full[e], use & 1, &acc_empty[e], ln_s, vdeg_row, 0u,
+                                         tl, e, n);
   }
 }
 

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_fused.cuh"
 #include "train_kernels.cuh"
 
 using namespace tspgnn;
@@ -139,6 +140,13 @@ struct tspgnn_ctx {
   float* d_biastab = nullptr;                 // [3][256] bias tables of K2's prologue
   bool fold = true;                           // tensor-core modes: inference timesteps use the folded output layer
   uint8_t* d_wmlp[3] = {nullptr, nullptr, nullptr};   // V_msg_E, E_msg_V, E_vote
+  // fused timestep kernel on CTA pairs (tc_fused.cuh): every B image split by output feature over the two CTAs
+  uint8_t* d_wl_pair[2] = {nullptr, nullptr};         // [0] folded V cell, [1] E cell: [rank][plane][kblock] x 16 KB
+  uint8_t* d_wm_pair[2] = {nullptr, nullptr};         // [0] V_msg_E, [1] E_msg_V:      [rank][layer][plane] x 4 KB
+  float *mV2 = nullptr, *xV2 = nullptr;               // second halves of the message double buffers
+  bool fused = false;                                 // tspgnn_step uses the fused kernel (tensor-core modes)
+  int dbg = 0;                                        // measurement aid of the fused kernel (FArgs::dbg; 4 = never any messages)
+  double v_pair_weight = 1.3;                         // cost of a vertex tile pair relative to an edge tile pair
   // plan
   int B = 0;
   int64_t nE = 0, nV = 0, nE_pad = 0, nV_pad = 0;
@@ -247,6 +255,8 @@ extern "C" int tspgnn_create(int d, int mode, int device, tspgnn_handle* out) {
   CUDA_TRY(cudaFuncSetAttribute(tc_lnlstm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Smem<2>::DYN_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tc_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Smem<1>::DYN_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tc_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Smem<2>::DYN_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::DYN_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(tc_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::DYN_BYTES));
   *out = h;
   return 0;
 }
@@ -265,6 +275,9 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
     for (void* p : wp)
       if (p) cudaFree(p);
   }
+  void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2};
+  for (void* p : fp)
+    if (p) cudaFree(p);
   void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg, h->d_lntab, h->d_biastab};
   for (void* p : tp)
     if (p) cudaFree(p);
@@ -277,6 +290,19 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
 }
 
 extern "C" int tspgnn_get_mode(tspgnn_handle h) { return h ? h->mode : TSPGNN_E_INVALID; }
+
+extern "C" int tspgnn_set_option(tspgnn_handle h, const char* name, double value) {
+  if (!h || !name) return fail(TSPGNN_E_INVALID, "NULL handle or option name");
+  const std::string key(name);
+  if (key == "fused") h->fused = value != 0.0;
+  else if (key == "v_pair_weight" && value > 0.0) h->v_pair_weight = value;
+  else if (key == "dbg") h->dbg = static_cast<int>(value);
+  else return fail(TSPGNN_E_INVALID, "unknown option '%s' (or bad value %g)", name, value);
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  drop_graphs(h);      // the captured timestep graphs bake the launch sequence in
+  return 0;
+}
 extern "C" int64_t tspgnn_sum_edges(tspgnn_handle h) { return h && h->has_plan ? h->nE : -1; }
 extern "C" int64_t tspgnn_sum_vertices(tspgnn_handle h) { return h && h->has_plan ? h->nV : -1; }
 extern "C" int64_t tspgnn_launch_count(tspgnn_handle h) { return h ? h->launches : -1; }
@@ -295,9 +321,12 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
   CUDA_TRY(cudaSetDevice(h->device));
   const ParamOffsets& o = h->po;
   if (upload_blob) {
-    if (dev_alloc(&h->d_params, n_floats)) return TSPGNN_E_CUDA;
+    // the blob size is fixed by d: allocate once, so that captured timestep graphs (which bake in
+    // pointers into d_params in SIMT mode) never see a dangling address
+    if (!h->d_params && dev_alloc(&h->d_params, n_floats)) return TSPGNN_E_CUDA;
     CUDA_TRY(cudaMemcpy(h->d_params, blob, n_floats * sizeof(float), cudaMemcpyHostToDevice));
   }
+  const int clamp_before[2] = {h->clamp_cell[0], h->clamp_cell[1]};
   // constant payloads
   for (int c = 0; c < 2; ++c)
     for (int g = 0; g < 5; ++g) {
@@ -317,6 +346,8 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
       }
     h->clamp_cell[c] = (bound[0] + bound[1] < 100.0) ? 0 : 1;
   }
+  // the clamp decisions are kernel arguments baked into the captured timestep graphs
+  if (clamp_before[0] != h->clamp_cell[0] || clamp_before[1] != h->clamp_cell[1]) drop_graphs(h);
   for (int m = 0; m < 2; ++m)
     for (int l = 0; l < 4; ++l) memcpy(h->h_bias[m].b[l], blob + o.msg_b[m][l], D * 4);
   for (int l = 0; l < 3; ++l) memcpy(h->h_bias[2].b[l], blob + o.vote_b[l], D * 4);
@@ -425,6 +456,36 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
       if (!h->d_wmlp[m] && dev_alloc(&h->d_wmlp[m], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
       CUDA_TRY(cudaMemcpy(h->d_wmlp[m], img.data(), img.size(), cudaMemcpyHostToDevice));
     }
+    // Images of the fused CTA-pair kernel: CTA `rank` of a pair holds output features
+    // [rank * N/2, (rank + 1) * N/2) of every B operand (tcgen05.mma.cta_group::2).
+    for (int c = 0; c < 2; ++c) {
+      // c == 0: kc still holds the folded vertex kernel [W4.Kx ; Kh] built above; c == 1: centred E kernel
+      if (c == 1)
+        for (int k = 0; k < 2 * D; ++k)
+          for (int g = 0; g < 4; ++g) {
+            const float* row = blob + o.cell_k[1] + static_cast<int64_t>(k) * 4 * D + g * D;
+            double m = 0.0;
+            for (int n = 0; n < D; ++n) m += row[n];
+            m /= D;
+            for (int n = 0; n < D; ++n) kc[static_cast<size_t>(k) * 4 * D + g * D + n] = static_cast<float>(row[n] - m);
+          }
+      img.assign(static_cast<size_t>(2) * hp * 2 * 16384, 0);
+      for (int r = 0; r < 2; ++r)
+        for (int p = 0; p < hp; ++p)
+          for (int kb = 0; kb < 2; ++kb)
+            make_b_image(kc.data(), 4 * D, kb * 64, r * 128, 128, p, img.data() + ((r * hp + p) * 2 + kb) * 16384);
+      if (!h->d_wl_pair[c] && dev_alloc(&h->d_wl_pair[c], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
+      CUDA_TRY(cudaMemcpy(h->d_wl_pair[c], img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
+    for (int m = 0; m < 2; ++m) {
+      img.assign(static_cast<size_t>(2) * 4 * hp * 4096, 0);
+      for (int r = 0; r < 2; ++r)
+        for (int l = 0; l < 4; ++l)
+          for (int p = 0; p < hp; ++p)
+            make_b_image(blob + o.msg_w[m][l], D, 0, r * 32, 32, p, img.data() + ((r * 4 + l) * hp + p) * 4096);
+      if (!h->d_wm_pair[m] && dev_alloc(&h->d_wm_pair[m], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
+      CUDA_TRY(cudaMemcpy(h->d_wm_pair[m], img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
   }
   h->has_params = true;
   h->snap_T = -1;   // snapshots of a training forward belong to the previous parameters
@@ -465,8 +526,10 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
   if (!edge_src || !edge_dst) return fail(TSPGNN_E_INVALID, "edge_src / edge_dst is NULL");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaDeviceSynchronize());
-  const int64_t nE_pad = (nE + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
-  const int64_t nV_pad = (nV + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+  // tensor-core modes: whole tile PAIRS (the fused kernel gives tile 2p + rank to CTA `rank` of a pair)
+  const int64_t pad_rows = (h->hp > 0) ? 2 * TILE_ROWS : TILE_ROWS;
+  const int64_t nE_pad = (nE + pad_rows - 1) / pad_rows * pad_rows;
+  const int64_t nV_pad = (nV + pad_rows - 1) / pad_rows * pad_rows;
   bool realloc_happened = false;
   if (nE_pad > h->cap_E) {
     realloc_happened = true;
@@ -489,7 +552,8 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
     if (h->hp == 0) {
       if (dev_alloc(&h->Vc, nV_pad * D)) return TSPGNN_E_CUDA;
     } else {
-      if (dev_alloc(&h->stateV, nV_pad / TILE_ROWS * tile_bytes(h->hp)) || dev_alloc(&h->d_deg, nV_pad))
+      if (dev_alloc(&h->stateV, nV_pad / TILE_ROWS * tile_bytes(h->hp)) || dev_alloc(&h->d_deg, nV_pad) ||
+          dev_alloc(&h->mV2, nV_pad * D) || dev_alloc(&h->xV2, nV_pad * D))
         return TSPGNN_E_CUDA;
     }
     h->cap_V = nV_pad;
@@ -516,6 +580,10 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
   if (realloc_happened || h->hp == 0) {
     CUDA_TRY(cudaMemsetAsync(h->xV, 0, nV_pad * D * 4, nullptr));
     CUDA_TRY(cudaMemsetAsync(h->mV, 0, nV_pad * D * 4, nullptr));
+    if (h->hp > 0) {
+      CUDA_TRY(cudaMemsetAsync(h->xV2, 0, nV_pad * D * 4, nullptr));
+      CUDA_TRY(cudaMemsetAsync(h->mV2, 0, nV_pad * D * 4, nullptr));
+    }
   }
   // The host-side validation below runs while the (pinned-memory) uploads above are in flight.  A batch
   // that fails it leaves the handle without a plan: the previous plan's buffers are already overwritten.
@@ -694,6 +762,69 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, bool fold, long long* tim
   return 0;
 }
 
+// One fused timestep on CTA pairs (tc_fused.cuh).  `phase` selects which halves of the message double
+// buffers are read (phase & 1) and written; `skip_mlp` = last timestep of a call.
+template <int HP>
+static int tc_launch_fused(tspgnn_ctx* h, cudaStream_t s, int phase, bool skip_mlp, long long* timeline = nullptr) {
+  FArgs a;
+  a.timeline = timeline;
+  a.stateE = h->stateE;
+  a.stateV = h->stateV;
+  a.wlE = h->d_wl_pair[1];
+  a.wlV = h->d_wl_pair[0];
+  a.wmE = h->d_wm_pair[1];
+  a.wmV = h->d_wm_pair[0];
+  float* mVb[2] = {h->mV, h->mV2};
+  float* xVb[2] = {h->xV, h->xV2};
+  a.mV_in = mVb[phase & 1];
+  a.mV_out = mVb[(phase + 1) & 1];
+  a.xV_in = xVb[phase & 1];
+  a.xV_out = xVb[(phase + 1) & 1];
+  a.src = h->d_src;
+  a.dst = h->d_dst;
+  a.nE = h->nE;
+  a.nV = h->nV;
+  a.pairsE = h->tilesE / 2;
+  a.pairsV = h->tilesV / 2;
+  a.clampV = h->clamp_cell[0];
+  a.clampE = h->clamp_cell[1];
+  a.skip_mlp = (skip_mlp || (h->dbg & 4)) ? 1 : 0;
+  a.dbg = h->dbg;
+  a.vdeg = h->d_deg;
+  a.ln_tab = h->d_lntab;
+  a.bias_tab = h->d_biastab;
+  // clusters are dedicated to edge or to vertex tile pairs; a vertex tile costs about 1.3 edge tiles
+  // (four MLP layers and the degree-bias pass against three layers and the scatter)
+  const int max_clusters = h->num_sms / 2;
+  int nclusters = std::min(max_clusters, a.pairsE + a.pairsV);
+  int ec = static_cast<int>(std::lround(static_cast<double>(nclusters) * a.pairsE / (a.pairsE + h->v_pair_weight * a.pairsV)));
+  ec = std::max(1, std::min(ec, nclusters - 1));
+  if (nclusters < 2) {
+    nclusters = 2;
+    ec = 1;
+  }
+  ec = std::min(ec, a.pairsE);
+  if (nclusters - ec > a.pairsV) nclusters = ec + a.pairsV;
+  a.e_clusters = ec;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nclusters);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = FSmem<HP>::DYN_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_step_kernel<HP>, a));
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
 static int simt_mlp(tspgnn_ctx* h, cudaStream_t s, const float* x, int64_t rows, int which, float* y) {
   const float* w = h->d_params + (which == 2 ? h->po.vote_w[0] : h->po.msg_w[which][0]);
   const int grid = std::max(1, std::min(2 * h->num_sms, grid_for(rows, SIMT_THREADS)));
@@ -743,6 +874,30 @@ static int one_step(tspgnn_ctx* h, cudaStream_t s) {
   return step_cells(h, s, h->fold);
 }
 
+static bool use_fused(const tspgnn_ctx* h) { return h->hp > 0 && h->fused && h->fold; }
+
+// n_steps iterations of while_body.  Tensor-core modes: one message launch for the current state, then
+// one fused launch per timestep (cell -> messages of the new state), the last one without messages;
+// both message double buffers are all-zero (xV) / dead (mV) again when the sequence ends.
+static int run_steps(tspgnn_ctx* h, cudaStream_t s, int n_steps) {
+  if (!use_fused(h)) {
+    for (int t = 0; t < n_steps; ++t)
+      if (one_step(h, s)) return TSPGNN_E_CUDA;
+    return 0;
+  }
+  if (step_messages(h, s, true)) return TSPGNN_E_CUDA;
+  for (int t = 0; t < n_steps; ++t) {
+    const int rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, t, t == n_steps - 1) : tc_launch_fused<1>(h, s, t, t == n_steps - 1);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int64_t launches_per_call(const tspgnn_ctx* h, int n_steps) {
+  if (h->hp == 0) return static_cast<int64_t>(n_steps) * 5;
+  return use_fused(h) ? n_steps + 1 : static_cast<int64_t>(n_steps) * 2;
+}
+
 extern "C" int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const float* dC, void* stream) {
   if (check_ready(h)) return TSPGNN_E_STATE;
   if (!dW || !dC) return fail(TSPGNN_E_INVALID, "W / C is NULL");
@@ -758,6 +913,7 @@ extern "C" int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const fl
     CUDA_TRY(cudaMemsetAsync(h->Vc, 0, h->nV_pad * D * 4, s));
   } else {
     CUDA_TRY(cudaMemsetAsync(h->xV, 0, h->nV_pad * D * 4, s));
+    CUDA_TRY(cudaMemsetAsync(h->xV2, 0, h->nV_pad * D * 4, s));
     if (h->hp == 2) {
       tc_edge_init_kernel<2><<<h->tilesE, TILE_ROWS, 0, s>>>(dW, dC, h->d_params + h->po.einit_w[0], h->nE, h->stateE);
       LAUNCH_CHECK(h);
@@ -786,18 +942,13 @@ extern "C" int tspgnn_step(tspgnn_handle h, int n_steps, void* stream) {
   if (n_steps == 0) return 0;
   // The per-step launch sequence is identical every timestep: capture it once per
   // (plan, n_steps) into a CUDA graph and replay it.  Legacy default stream cannot capture.
-  if (s == nullptr || n_steps < 2) {
-    for (int t = 0; t < n_steps; ++t)
-      if (one_step(h, s)) return TSPGNN_E_CUDA;
-    return 0;
-  }
+  if (s == nullptr || n_steps < 2) return run_steps(h, s, n_steps);
   auto it = h->step_graphs.find(n_steps);
   if (it == h->step_graphs.end()) {
     cudaGraph_t graph = nullptr;
     const int64_t before = h->launches;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    int rc = 0;
-    for (int t = 0; t < n_steps && !rc; ++t) rc = one_step(h, s);
+    const int rc = run_steps(h, s, n_steps);
     cudaError_t e = cudaStreamEndCapture(s, &graph);
     h->launches = before;
     if (rc) {
@@ -812,7 +963,7 @@ extern "C" int tspgnn_step(tspgnn_handle h, int n_steps, void* stream) {
     it = h->step_graphs.emplace(n_steps, exec).first;
   }
   CUDA_TRY(cudaGraphLaunch(it->second, s));
-  h->launches += static_cast<int64_t>(n_steps) * (h->hp == 0 ? 5 : 2);
+  h->launches += launches_per_call(h, n_steps);
   return 0;
 }
 
@@ -915,7 +1066,7 @@ extern "C" int tspgnn_set_states(tspgnn_handle h, const float* dVh, const float*
 extern "C" int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* mean_ms, void* stream) {
   if (check_ready(h)) return TSPGNN_E_STATE;
   if (h->hp == 0) return fail(TSPGNN_E_UNSUPPORTED, "tspgnn_time_kernel needs a tensor-core mode");
-  if (which < 0 || which > 1 || iters <= 0 || !mean_ms) return fail(TSPGNN_E_INVALID, "bad which / iters / mean_ms");
+  if (which < 0 || which > 2 || iters <= 0 || !mean_ms) return fail(TSPGNN_E_INVALID, "bad which / iters / mean_ms");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   if (upload_constants(h, s)) return TSPGNN_E_CUDA;
@@ -923,6 +1074,25 @@ extern "C" int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* 
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
   double total = 0.0;
+  if (which == 2) {
+    // the fused timestep kernel: messages of the current state first, then `iters` timed launches
+    // that alternate the message double buffers, then one launch without messages (buffers clean again)
+    if (step_messages(h, s, true)) return TSPGNN_E_CUDA;
+    for (int i = 0; i <= iters; ++i) {
+      CUDA_TRY(cudaEventRecord(e0, s));
+      const int rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, i, i == iters) : tc_launch_fused<1>(h, s, i, i == iters);
+      if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(e1, s));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+      if (i < iters) total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *mean_ms = static_cast<float>(total / iters);
+    return 0;
+  }
   for (int i = 0; i < iters; ++i) {
     // keep the producer/consumer pairing of xV intact: the kernel that is not timed runs untimed
     if (which == 0) {
@@ -965,7 +1135,12 @@ extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_
   CUDA_TRY(cudaMalloc(&d, need * 8));
   CUDA_TRY(cudaMemsetAsync(d, 0, need * 8, s));
   int rc;
-  if (which == 0) {
+  if (which == 2) {
+    // fused timestep kernel: messages, one traced launch, one launch without messages (buffers clean again)
+    rc = step_messages(h, s, true);
+    if (!rc) rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, 0, false, d) : tc_launch_fused<1>(h, s, 0, false, d);
+    if (!rc) rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, 1, true) : tc_launch_fused<1>(h, s, 1, true);
+  } else if (which == 0) {
     rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold) : tc_launch_k2<1>(h, s, false, h->fold);
     if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold, d) : tc_launch_k1<1>(h, s, h->fold, d);
   } else {

@@ -50,6 +50,33 @@ class Engine(object):
         s = stream if stream is not None else self.stream()
         return ctypes.c_void_p(s.cuda_stream)
 
+    def _order_in(self, stream, *tensors):
+        """Caller tensors are produced on torch's current stream; the engine launches on its own
+        (non-blocking) stream.  Make the engine stream wait for the current one and tell the caching
+        allocator that the tensors are in use there, so neither a read-before-write nor a premature
+        reuse of their memory can happen."""
+        import torch
+        s = stream if stream is not None else self.stream()
+        cur = torch.cuda.current_stream(self.device)
+        if cur != s:
+            s.wait_stream(cur)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(s)
+        return s
+
+    def _order_out(self, stream):
+        """Results written on the engine stream become visible to work queued later on torch's current stream."""
+        import torch
+        s = stream if stream is not None else self.stream()
+        cur = torch.cuda.current_stream(self.device)
+        if cur != s:
+            cur.wait_stream(s)
+
+    def set_option(self, name, value):
+        """Tuning / diagnosis knobs of include/tspgnn.h (e.g. ``fused`` 0/1)."""
+        _lib.check(_lib.lib.tspgnn_set_option(self._h, name.encode(), float(value)))
+
     # -- parameters / plan --------------------------------------------------------
     def set_params(self, params):
         blob = params if isinstance(params, np.ndarray) else flatten(params, self.d)
@@ -84,11 +111,14 @@ class Engine(object):
         return logits, preds
 
     def forward_device(self, dW, dC, time_steps, d_logits, d_preds, stream=None):
+        self._order_in(stream, dW, dC, d_logits, d_preds)
         _lib.check(_lib.lib.tspgnn_forward_device(self._h, ctypes.c_void_p(dW.data_ptr()), ctypes.c_void_p(dC.data_ptr()),
                                                   int(time_steps), ctypes.c_void_p(d_logits.data_ptr()),
                                                   ctypes.c_void_p(d_preds.data_ptr()), self._sptr(stream)))
+        self._order_out(stream)
 
     def init_embeddings(self, dW, dC, stream=None):
+        self._order_in(stream, dW, dC)
         _lib.check(_lib.lib.tspgnn_init_embeddings(self._h, ctypes.c_void_p(dW.data_ptr()),
                                                    ctypes.c_void_p(dC.data_ptr()), self._sptr(stream)))
 
@@ -96,8 +126,10 @@ class Engine(object):
         _lib.check(_lib.lib.tspgnn_step(self._h, int(n_steps), self._sptr(stream)))
 
     def readout(self, d_logits, d_preds, stream=None):
+        self._order_in(stream, d_logits, d_preds)
         _lib.check(_lib.lib.tspgnn_readout(self._h, ctypes.c_void_p(d_logits.data_ptr()),
                                            ctypes.c_void_p(d_preds.data_ptr()), self._sptr(stream)))
+        self._order_out(stream)
 
     def get_states(self, stream=None):
         """{'V': (c,h), 'E': (c,h)} as row-major fp32 torch tensors on the device."""
@@ -114,7 +146,7 @@ class Engine(object):
         return {"V": (Vc, Vh), "E": (Ec, Eh)}
 
     def set_states(self, Vh=None, Vc=None, Eh=None, Ec=None, stream=None):
-        s = stream if stream is not None else self.stream()
+        s = self._order_in(stream, Vh, Vc, Eh, Ec)
         ptrs = [ctypes.c_void_p(t.data_ptr()) if t is not None else None for t in (Vh, Vc, Eh, Ec)]
         _lib.check(_lib.lib.tspgnn_set_states(self._h, *ptrs, self._sptr(s)))
         s.synchronize()
@@ -141,10 +173,12 @@ class Engine(object):
 
     def train_forward(self, dW, dC, time_steps, d_logits=None, d_preds=None, stream=None):
         """Forward pass that keeps the per-timestep state the reverse pass needs (device tensors)."""
+        self._order_in(stream, dW, dC, d_logits, d_preds)
         _lib.check(_lib.lib.tspgnn_train_forward(
             self._h, ctypes.c_void_p(dW.data_ptr()), ctypes.c_void_p(dC.data_ptr()), int(time_steps),
             ctypes.c_void_p(d_logits.data_ptr()) if d_logits is not None else None,
             ctypes.c_void_p(d_preds.data_ptr()) if d_preds is not None else None, self._sptr(stream)))
+        self._order_out(stream)
 
     def backward(self, d_route_exists, global_batch=0, stream=None):
         """Loss and flat gradient blob (device tensors) of the last train_forward.  ``global_batch``
@@ -152,18 +186,20 @@ class Engine(object):
         whole batch and sum (all-reduce) the returned blobs."""
         import torch
         dev = torch.device("cuda", self.device)
-        s = stream if stream is not None else self.stream()
+        s = self._order_in(stream, d_route_exists)
         with torch.cuda.stream(s):
             grads = torch.empty(self.param_count, dtype=torch.float32, device=dev)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
         _lib.check(_lib.lib.tspgnn_backward(self._h, ctypes.c_void_p(d_route_exists.data_ptr()), int(global_batch),
                                             ctypes.c_void_p(grads.data_ptr()), ctypes.c_void_p(loss.data_ptr()),
                                             self._sptr(s)))
+        self._order_out(s)
         return loss, grads
 
     def apply_gradients(self, d_grads, stream=None):
         """L2 term + clip_by_global_norm + Adam (model.py:160-167); returns the global norm."""
         norm = ctypes.c_float(0)
+        self._order_in(stream, d_grads)
         _lib.check(_lib.lib.tspgnn_apply_gradients(self._h, ctypes.c_void_p(d_grads.data_ptr()), ctypes.byref(norm),
                                                    self._sptr(stream)))
         return float(norm.value)
@@ -196,7 +232,7 @@ class Engine(object):
         _lib.check(_lib.lib.tspgnn_set_optimizer_state(self._h, _np_ptr(m), _np_ptr(v), int(state["step"]), m.size))
 
     def time_kernel(self, which, iters, stream=None):
-        """Mean device time (ms) of one launch of K1 (which=0) or K2 (which=1)."""
+        """Mean device time (ms) of one launch of K1 (which=0), K2 (which=1) or the fused timestep kernel (which=2)."""
         ms = ctypes.c_float(0)
         _lib.check(_lib.lib.tspgnn_time_kernel(self._h, int(which), int(iters), ctypes.byref(ms), self._sptr(stream)))
         return float(ms.value)
