@@ -18,11 +18,13 @@
 //
 // Warp roles per CTA (384 threads), both CTAs of the pair run the same program on their own tile
 // (tile 2p + rank of tile pair p):
-//   warps 0-3, 4-7 : two chain warpgroups, tile n -> warpgroup n & 1; thread = row = TMEM lane.
-//                    cell epilogue (k1_cell_tile) -> MLP layer epilogues -> scatter / store
-//   warp  8        : even CTA: issues every tcgen05.mma of the pair (event driven, f_mma); odd CTA: forwards
+//   warp  0        : even CTA: issues every tcgen05.mma of the pair (event driven, f_mma); odd CTA: forwards
 //                    its operand barriers (weights, h planes, x operand) to their twins in the even CTA
-//   warps 9-11     : producers of the x operand (gather / read-and-clear)
+//   warps 1-3      : producers of the x operand (gather / read-and-clear)
+//   warps 4-7, 8-11: two chain warpgroups, tile g -> warpgroup g & 1; thread = row = TMEM lane.
+//                    cell epilogue (k1_cell_tile) -> MLP layer epilogues -> scatter / store
+//   (the chain warps carry the critical path and get the higher warp ids: the scheduler prefers them, so
+//   the gather fills issue slots instead of taking them)
 // Shared-memory slots (32 KB each): slot 0 = x operand; slots 1.. = ring of h slots.  A tile's h
 // slot is its home for the whole chain: h planes (bulk copy) -> A operand of the LSTM MMA -> new h'
 // planes (written by the cell epilogue) -> hidden activations of every MLP layer, in place -> fp32
@@ -42,22 +44,53 @@ struct FArgs {
   const uint8_t* wlV;     //   (vertex cell with the folded E_msg_V output layer)
   const uint8_t* wmE;     // MLP images per CTA rank: [rank][layer][plane] x (32 features x 64 k bf16) = 4 KB each
   const uint8_t* wmV;
-  const float* mV_in;     // vertex messages of the previous launch [sumV][64]
-  float* mV_out;
-  float* xV_in;           // summed edge activations of the previous launch; read and cleared by vertex tiles
-  float* xV_out;
+  // message double buffers: timestep t reads half t & 1 and writes half (t + 1) & 1
+  float* mVb[2];          // vertex messages [sumV][64]
+  float* xVb[2];          // summed edge activations; read and cleared by vertex tiles
   const int32_t* src;
   const int32_t* dst;
   int64_t nE, nV;
   int pairsE, pairsV;     // tile pairs (the state images are allocated for 2 * pairs tiles)
   int e_clusters;         // clusters [0, e_clusters) own edge tile pairs, the others vertex tile pairs
   int clampE, clampV;
-  int skip_mlp;           // last timestep of a call: nobody consumes the messages
-  int dbg;                // measurement aid (results are wrong when set): 1 = no reductions, 2 = no scatter / store
+  int n_steps;            // timesteps of this launch (the kernel is persistent over them)
+  int skip_last_mlp;      // nobody consumes the messages of the state after the last timestep
+  int dbg;                // measurement aid (results are wrong when set): 1 = no reductions, 2 = no scatter / store,
+                          // 4 = never any messages
+  unsigned int* grid_ctr; // grid barrier between timesteps; zero at launch (cleared by the message kernel before)
   const float* vdeg;
   const float* ln_tab;
   const float* bias_tab;
   long long* timeline;
+};
+
+// Grid-wide barrier between two timesteps of the persistent kernel (every CTA is resident: the grid
+// never exceeds the SM count).  Same pattern as cooperative groups' grid sync: CTA barrier, one thread
+// publishes (release) and polls (acquire) a counter in global memory, CTA barrier.  The gpu-scope
+// fences also invalidate this SM's L1, so the messages other SMs wrote are re-read from L2.
+__device__ __forceinline__ void f_grid_sync(unsigned int* ctr, unsigned int target) {
+  ptx::tcgen05_fence_before();
+  asm volatile("bar.sync 0;" ::: "memory");
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const long long t0 = clock64();
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+      if (clock64() - t0 > 4000000000LL) __trap();      // a CTA that is not resident would hang the grid: fail loudly
+    } while (seen < target);
+    __threadfence();
+  }
+  asm volatile("bar.sync 0;" ::: "memory");
+  ptx::tcgen05_fence_after();
+}
+
+// per-CTA geometry of the persistent loop
+struct FGeo {
+  int p0, rank, ntiles, nh, n_steps, nl_full, skip_last, nctas;
+  __device__ __forceinline__ int nl(int t) const { return (skip_last && t == n_steps - 1) ? 0 : nl_full; }
+  __device__ __forceinline__ int tile(int n) const { return 2 * (p0 + n) + rank; }
 };
 
 template <int HP>
@@ -119,29 +152,33 @@ __device__ __forceinline__ FBars f_bars(uint8_t* base) {
 
 // ---- MMA issuer (even CTA) -----------------------------------------------------------------------
 // Event driven: the two chain warpgroups are two independent streams of MMA work,
-//     stream e:  [ layer 0 .. nl-1 of tile n,  LSTM(n + 2) ]  for n = e, e + 2, ...
+//     stream e:  [ layer 0 .. nl-1 of tile g,  LSTM(g + 2) ]  for the tiles g with g & 1 == e
 // and the issuer serves whichever stream's next item is ready (non-blocking mbarrier tests), so a
 // warpgroup in its latency-critical layer chain never queues behind the other one's items.  (A
 // fixed issue order made the issuer the critical path: every layer step costs ~3 k cycles of
 // epilogue + synchronisation latency, during which the other stream's requests waited.)  LSTM items are
 // issued in tile order (the x operand slot is filled in tile order).
+// Tiles are numbered g = t * ntiles + n over the whole launch: warpgroup, accumulator half, h slot and
+// every barrier parity follow from g, so nothing is re-initialised between timesteps.
 // act_ready[e] counts the four warps of warpgroup e of BOTH CTAs (the odd CTA's warps arrive remotely),
 // the h / x operand barriers of the odd CTA are forwarded by its warp 8 (f_forward).
 template <int HP>
-__device__ __forceinline__ void f_mma(uint8_t* smem, const FBars& b, uint32_t tmem, int ntiles, int nl, int nh,
-                                      long long* tl_) {
+__device__ __forceinline__ void f_mma(const FArgs& a, uint8_t* smem, const FBars& b, uint32_t tmem, const FGeo& geo) {
   using L = FSmem<HP>;
   constexpr uint32_t IDESC_LSTM = ptx::umma_idesc_bf16(256, 256);
   constexpr uint32_t IDESC_MLP = ptx::umma_idesc_bf16(256, 64);
   constexpr int NCOMB = (HP == 2) ? 3 : 1;
-  long long* tl = ptx::elect_one() ? tl_ : nullptr;
+  const bool leader_lane = ptx::elect_one();
+  const int nh = geo.nh, ntiles = geo.ntiles;
   const uint64_t slot_desc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(smem + L::SLOT_OFF), 2048, 128);
   const uint64_t wl_desc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(smem + L::WL_OFF), 2048, 128);
   const uint64_t wm_desc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(smem + L::WM_OFF), 512, 128);
+  long long* tl = nullptr;
+  int gbase = 0;       // first tile number of the current timestep (for the trace only)
 
-  // one k-block (h: half 0, x: half 1) of the LSTM contraction of tile n
-  auto issue_lstm_half = [&](int n, int half) {
-    const int e = n & 1, hs = n % nh;
+  // one k-block (h: half 0, x: half 1) of the LSTM contraction of tile g
+  auto issue_lstm_half = [&](int g, int half) {
+    const int e = g & 1, hs = g % nh;
     const uint32_t d_tmem = tmem + e * 256;
     const int kb = 1 - half;      // the h k-block first: its bulk copy lands long before the gathered x operand is built
     ptx::tcgen05_fence_after();
@@ -164,131 +201,151 @@ __device__ __forceinline__ void f_mma(uint8_t* smem, const FBars& b, uint32_t tm
       }
     }
     __syncwarp();
-    tl_mark(tl, 2, n, 1 + half);
+    tl_mark(tl, 2, g - gbase, 1 + half);
   };
-  auto h_ready = [&](int n) {
-    const int hs = n % nh;
-    const uint32_t par = (n / nh) & 1;
+  auto h_ready = [&](int g) {
+    const int hs = g % nh;
+    const uint32_t par = (g / nh) & 1;
     return ptx::mbar_test(&b.h_full[hs], par) && ptx::mbar_test(&b.p_h_full[hs], par);
   };
-  auto x_ready = [&](int n) {
-    return ptx::mbar_test(b.x_full, n & 1) && ptx::mbar_test(b.p_x_full, n & 1);
-  };
+  auto x_ready = [&](int g) { return ptx::mbar_test(b.x_full, g & 1) && ptx::mbar_test(b.p_x_full, g & 1); };
 
   ptx::mbar_wait(b.w, 0);
   ptx::mbar_wait(b.p_w, 0);
-  // per stream: tile, next layer (nl = the LSTM item of tile + 2), act_ready phases consumed, and
-  // whether the h k-block of the pending LSTM item has been issued
-  int tile_[2] = {0, 1}, layer_[2] = {0, 0};
-  uint32_t ar[2] = {0, 0};
-  bool active[2] = {ntiles > 0, ntiles > 1};
-  // LSTM items in flight, strictly in tile order: lstm_n = next tile whose LSTM has to be issued,
-  // lstm_h = its h k-block is already issued; the first two tiles need no drained accumulator
-  int lstm_n = 0;
-  bool lstm_h = false;
-  int drained_ok = (ntiles > 1) ? 2 : 1;        // LSTM items below this tile index may be issued
-  long long spin0 = clock64();
-  int nap = 0;
-  while (active[0] || active[1] || lstm_n < drained_ok) {
-    bool progress = false;
-    // ---- the LSTM item at the head of the tile order ----
-    if (lstm_n < drained_ok) {
-      if (!lstm_h) {
-        if (h_ready(lstm_n)) {
-          tl_mark(tl, 2, lstm_n, 0);
-          issue_lstm_half(lstm_n, 0);
-          lstm_h = true;
-          progress = true;
-        }
-      } else if (x_ready(lstm_n)) {
-        issue_lstm_half(lstm_n, 1);
-        lstm_h = false;
-        ++lstm_n;
-        progress = true;
-      }
-    }
-    // ---- the layer chains ----
+  uint32_t ar[2] = {0, 0};      // act_ready phases consumed per stream, over the whole launch
+  for (int t = 0; t < geo.n_steps; ++t) {
+    const int nl = (a.dbg & 4) ? 0 : geo.nl(t);
+    const int base = t * ntiles, end = base + ntiles;
+    gbase = base;
+    tl = (t == 0 && leader_lane) ? a.timeline : nullptr;
+    // per stream: tile, next layer (nl = the LSTM item of tile + 2 comes next)
+    int tile_[2], layer_[2] = {0, 0};
+    bool active[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      if (!active[e]) continue;
-      const int n = tile_[e];
-      if (layer_[e] < nl) {
-        if (!ptx::mbar_test(&b.act_ready[e], ar[e] & 1)) continue;
-        ++ar[e];
-        const int l = layer_[e], hs = n % nh;
-        ptx::tcgen05_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t adesc = slot_desc0 + static_cast<uint32_t>(((1 + hs) * L::SLOT_BYTES) >> 4);
-          const uint64_t bdesc = wm_desc0 + static_cast<uint32_t>((l * L::WM_LAYER) >> 4);
-          const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
-#pragma unroll
-          for (int cb = 0; cb < NCOMB; ++cb) {
-            const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16_ss_pair(tmem + e * 256, adesc + ((pa * PLANE_BYTES + k * 4096) >> 4),
-                                     bdesc + ((pb * 4096 + k * 1024) >> 4), IDESC_MLP, (cb | k) ? 1u : 0u);
+      tile_[e] = base + ((e ^ base) & 1);
+      active[e] = tile_[e] < end;
+    }
+    const bool had[2] = {active[0], active[1]};
+    // LSTM items strictly in tile order: lstm_g = next tile whose LSTM has to be issued, lstm_h = its h
+    // k-block is already issued; the first two tiles of a timestep need no drained accumulator
+    int lstm_g = base;
+    bool lstm_h = false;
+    int drained_ok = (ntiles > 1) ? base + 2 : base + 1;      // LSTM items below this tile number may be issued
+    long long spin0 = clock64();
+    int nap = 0;
+    while (active[0] || active[1] || lstm_g < drained_ok) {
+      bool progress = false;
+      // ---- the LSTM item at the head of the tile order ----
+      if (lstm_g < drained_ok) {
+        if (!lstm_h) {
+          if (h_ready(lstm_g)) {
+            tl_mark(tl, 2, lstm_g - gbase, 0);
+            issue_lstm_half(lstm_g, 0);
+            lstm_h = true;
+            progress = true;
           }
-          ptx::umma_commit_pair(&b.acc_full[e]);
-        }
-        __syncwarp();
-        if (l < 4) tl_mark(tl, 2, n, 3 + l);
-        ++layer_[e];
-        progress = true;
-      } else {
-        // the chain of tile n is issued; its accumulator half is reusable once the warpgroup has drained it
-        if (n + 2 >= ntiles) {
-          active[e] = false;        // (the last drained arrival of a stream is not consumed)
+        } else if (x_ready(lstm_g)) {
+          issue_lstm_half(lstm_g, 1);
+          lstm_h = false;
+          ++lstm_g;
           progress = true;
-          continue;
         }
-        if (drained_ok != n + 2) continue;      // the other stream's LSTM item comes first in tile order
-        if (!ptx::mbar_test(&b.act_ready[e], ar[e] & 1)) continue;
-        ++ar[e];
-        drained_ok = n + 3;
-        tile_[e] = n + 2;
-        layer_[e] = 0;
-        progress = true;
+      }
+      // ---- the layer chains ----
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (!active[e]) continue;
+        const int g = tile_[e];
+        if (layer_[e] < nl) {
+          if (!ptx::mbar_test(&b.act_ready[e], ar[e] & 1)) continue;
+          ++ar[e];
+          const int l = layer_[e], hs = g % nh;
+          ptx::tcgen05_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t adesc = slot_desc0 + static_cast<uint32_t>(((1 + hs) * L::SLOT_BYTES) >> 4);
+            const uint64_t bdesc = wm_desc0 + static_cast<uint32_t>((l * L::WM_LAYER) >> 4);
+            const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
+#pragma unroll
+            for (int cb = 0; cb < NCOMB; ++cb) {
+              const int pa = (HP == 2) ? pa_[cb] : 0, pb = (HP == 2) ? pb_[cb] : 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16_ss_pair(tmem + e * 256, adesc + ((pa * PLANE_BYTES + k * 4096) >> 4),
+                                       bdesc + ((pb * 4096 + k * 1024) >> 4), IDESC_MLP, (cb | k) ? 1u : 0u);
+            }
+            ptx::umma_commit_pair(&b.acc_full[e]);
+          }
+          __syncwarp();
+          if (l < 4) tl_mark(tl, 2, g - gbase, 3 + l);
+          ++layer_[e];
+          progress = true;
+        } else {
+          // the chain of tile g is issued; its accumulator half is reusable once the warpgroup has drained it
+          if (g + 2 >= end) {
+            active[e] = false;        // (the stream's last drained arrival of the timestep is consumed below)
+            progress = true;
+            continue;
+          }
+          if (drained_ok != g + 2) continue;      // the other stream's LSTM item comes first in tile order
+          if (!ptx::mbar_test(&b.act_ready[e], ar[e] & 1)) continue;
+          ++ar[e];
+          drained_ok = g + 3;
+          tile_[e] = g + 2;
+          layer_[e] = 0;
+          progress = true;
+        }
+      }
+      if (progress) {
+        spin0 = clock64();
+      } else {
+        // nothing ready: sleep on a layer-chain barrier instead of spinning (this warp shares its
+        // scheduler with a warp of each chain warpgroup), alternating between the two streams
+        nap ^= 1;
+        const int e = (active[nap] && layer_[nap] < nl) ? nap : nap ^ 1;
+        if (active[e] && layer_[e] < nl) ptx::mbar_try_wait_ns(&b.act_ready[e], ar[e] & 1, 160);
+        else __nanosleep(100);
+        if (clock64() - spin0 > 4000000000LL) __trap();      // protocol bug: fail loudly instead of hanging
       }
     }
-    if (progress) {
-      spin0 = clock64();
-    } else {
-      // nothing ready: sleep on a layer-chain barrier instead of spinning (this warp shares its
-      // scheduler with a warp of each chain warpgroup), alternating between the two streams
-      nap ^= 1;
-      const int e = (active[nap] && layer_[nap] < nl) ? nap : nap ^ 1;
-      if (active[e] && layer_[e] < nl) ptx::mbar_try_wait_ns(&b.act_ready[e], ar[e] & 1, 160);
-      else __nanosleep(100);
-      if (clock64() - spin0 > 4000000000LL) __trap();      // protocol bug: fail loudly instead of hanging
-    }
+    // the last tile of each stream: its drained arrival closes the stream's phase count for this timestep
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (had[e]) {
+        ptx::mbar_wait(&b.act_ready[e], ar[e] & 1);
+        ++ar[e];
+      }
+    if (t + 1 < geo.n_steps) f_grid_sync(a.grid_ctr, static_cast<unsigned int>(t + 1) * geo.nctas);
   }
 }
 
 // ---- odd CTA, warp 8: forwards its operand barriers to the twins in the even CTA -----------------
-__device__ __forceinline__ void f_forward(const FBars& b, int ntiles, int nh) {
+__device__ __forceinline__ void f_forward(const FArgs& a, const FBars& b, const FGeo& geo) {
   auto forward = [&](uint64_t* local, uint64_t* twin, uint32_t parity) {
     ptx::mbar_wait(local, parity);
     if (ptx::elect_one()) ptx::mbar_arrive_remote(ptx::mapa_u32(ptx::smem_u32(twin), 0));
     __syncwarp();
   };
   forward(b.w, b.p_w, 0);
-  for (int n = 0; n < ntiles; ++n) {
-    const int hs = n % nh;
-    forward(&b.h_full[hs], &b.p_h_full[hs], (n / nh) & 1);
-    forward(b.x_full, b.p_x_full, n & 1);
+  for (int t = 0; t < geo.n_steps; ++t) {
+    for (int n = 0; n < geo.ntiles; ++n) {
+      const int g = t * geo.ntiles + n, hs = g % geo.nh;
+      forward(&b.h_full[hs], &b.p_h_full[hs], (g / geo.nh) & 1);
+      forward(b.x_full, b.p_x_full, g & 1);
+    }
+    if (t + 1 < geo.n_steps) f_grid_sync(a.grid_ctr, static_cast<unsigned int>(t + 1) * geo.nctas);
   }
 }
 
 // ---- producers of the x operand (single slot) --------------------------------------------------
 template <int HP, bool IS_V>
-__device__ __forceinline__ void f_producer(const FArgs& a, uint8_t* xslot, const FBars& b, int p0, int rank, int ntiles,
-                                           int gw, int lane) {
-  long long* tl = (gw == 0 && lane == 0) ? a.timeline : nullptr;
+__device__ __forceinline__ void f_producer(const FArgs& a, uint8_t* smem, const FBars& b, const FGeo& geo, int gw,
+                                           int lane) {
+  using L = FSmem<HP>;
+  uint8_t* xslot = smem + L::SLOT_OFF;
+  uint8_t* state = IS_V ? a.stateV : a.stateE;
   const int r8 = lane & 7;
-  int si[6], di[6];
-#pragma unroll
-  for (int gi = 0; gi < 6; ++gi) si[gi] = di[gi] = 0;
+  const int ntiles = geo.ntiles;
   auto load_idx = [&](int tile, int (&s)[6], int (&d)[6]) {
     if (IS_V) return;
     const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
@@ -301,177 +358,218 @@ __device__ __forceinline__ void f_producer(const FArgs& a, uint8_t* xslot, const
       }
     }
   };
-  if (ntiles > 1) load_idx(2 * (p0 + 1) + rank, si, di);       // (tile 0: built by the chain warps)
-  for (int n = 0; n < ntiles; ++n) {
-    const int tile = 2 * (p0 + n) + rank;
-    int sn[6], dn[6];
-#pragma unroll
-    for (int gi = 0; gi < 6; ++gi) sn[gi] = dn[gi] = 0;
-    if (n >= 1 && n + 1 < ntiles) load_idx(tile + 2, sn, dn);   // next tile's column indices, a tile ahead
-    tl_mark(tl, 3, n, 0);
-    if (n >= 1) ptx::mbar_wait(b.x_empty, (n - 1) & 1);
-    tl_mark(tl, 3, n, 1);
-    if (n == 0) {
-      if (gw == 0) ptx::mbar_wait(b.boot, 0);
-    } else {
-      k1_fill_x<HP, IS_V>(xslot, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, a.mV_in, a.xV_in, si, di);
-      ptx::fence_proxy_async_smem();
-#pragma unroll
-      for (int gi = 0; gi < 6; ++gi) {
-        si[gi] = sn[gi];
-        di[gi] = dn[gi];
+  for (int t = 0; t < geo.n_steps; ++t) {
+    long long* tl = (t == 0 && gw == 0 && lane == 0) ? a.timeline : nullptr;
+    const float* mV_in = a.mVb[t & 1];
+    float* xV_in = a.xVb[t & 1];
+    const int base = t * ntiles;
+    if (gw == 0 && lane == 0) {
+      // h planes of the first tiles of the timestep (every slot is free: the previous timestep is
+      // complete); later ones are fetched by the warpgroup that retires a slot
+      for (int n = 0; n < ntiles && n < geo.nh; ++n) {
+        const int hs = (base + n) % geo.nh;
+        ptx::mbar_arrive_expect_tx(&b.h_full[hs], HP * PLANE_BYTES);
+        ptx::bulk_g2s(smem + L::SLOT_OFF + (1 + hs) * L::SLOT_BYTES,
+                      state + static_cast<int64_t>(geo.tile(n)) * tile_bytes(HP), HP * PLANE_BYTES, &b.h_full[hs]);
       }
     }
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(b.x_full);
-    tl_mark(tl, 3, n, 2);
+    int si[6], di[6];
+#pragma unroll
+    for (int gi = 0; gi < 6; ++gi) si[gi] = di[gi] = 0;
+    if (ntiles > 1) load_idx(geo.tile(1), si, di);       // (tile 0: built by the chain warps)
+    for (int n = 0; n < ntiles; ++n) {
+      const int tile = geo.tile(n), g = base + n;
+      int sn[6], dn[6];
+#pragma unroll
+      for (int gi = 0; gi < 6; ++gi) sn[gi] = dn[gi] = 0;
+      if (n >= 1 && n + 1 < ntiles) load_idx(tile + 2, sn, dn);   // next tile's column indices, a tile ahead
+      tl_mark(tl, 3, n, 0);
+      if (n >= 1) ptx::mbar_wait(b.x_empty, (g - 1) & 1);
+      tl_mark(tl, 3, n, 1);
+      if (n == 0) {
+        if (gw == 0) ptx::mbar_wait(b.boot, t & 1);
+      } else {
+        k1_fill_x<HP, IS_V, false>(xslot, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, mV_in, xV_in, si, di);
+        ptx::fence_proxy_async_smem();
+#pragma unroll
+        for (int gi = 0; gi < 6; ++gi) {
+          si[gi] = sn[gi];
+          di[gi] = dn[gi];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(b.x_full);
+      tl_mark(tl, 3, n, 2);
+    }
+    if (t + 1 < geo.n_steps) f_grid_sync(a.grid_ctr, static_cast<unsigned int>(t + 1) * geo.nctas);
   }
 }
 
 // ---- chain warpgroups -----------------------------------------------------------------------------
-// ROLE: false = edge tiles (three hidden layers, scatter-add of a3), true = vertex tiles (four layers,
+// IS_V: false = edge tiles (three hidden layers, scatter-add of a3), true = vertex tiles (four layers,
 // message store).
 template <int HP, bool IS_V, bool CLAMP>
-__device__ __forceinline__ void f_chain(const FArgs& a, uint8_t* smem, const FBars& b, uint32_t tmem, int p0, int rank,
-                                        int ntiles, int warp, int lane, uint32_t ln_s, uint32_t bias_s) {
+__device__ __forceinline__ void f_chain(const FArgs& a, uint8_t* smem, const FBars& b, uint32_t tmem, const FGeo& geo,
+                                        int warp, int lane, uint32_t ln_s, uint32_t bias_s) {
   using L = FSmem<HP>;
   constexpr int NL = IS_V ? 4 : 3;
   constexpr int NH = IS_V ? L::NH_V : L::NH_E;
-  const int nl = a.skip_mlp ? 0 : NL;
-  const int e = warp >> 2, q4 = warp & 3;
+  const int e = (warp >> 2) - 1, q4 = warp & 3;
   const int r = q4 * 32 + lane;
-  long long* tl = (q4 == 0 && lane == 0) ? a.timeline : nullptr;
+  const int ntiles = geo.ntiles;
   const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 256;
   uint8_t* state = IS_V ? a.stateV : a.stateE;
   const int64_t n_rows = IS_V ? a.nV : a.nE;
   const uint32_t slots_s = ptx::smem_u32(smem + L::SLOT_OFF);
   // the issuer lives in the even CTA: every warp of this warpgroup of BOTH CTAs arrives on its act_ready[e]
   const uint32_t act_ready_leader = ptx::mapa_u32(ptx::smem_u32(&b.act_ready[e]), 0);
-  uint32_t af = 0;              // acc_full phases consumed by this warpgroup
-  for (int n = e; n < ntiles; n += 2) {
-    const int tile = 2 * (p0 + n) + rank;
-    const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
-    const int hs = n % NH;
-    const uint32_t b_s = slots_s + (1 + hs) * L::SLOT_BYTES;
-    uint8_t* gtile = state + static_cast<int64_t>(tile) * tile_bytes(HP);
-    // endpoints of this warp's 32 rows, fetched a whole chain ahead of the scatter that uses them
-    int my_s = -1, my_d = -1;
-    if (!IS_V && nl > 0 && row0 + r < n_rows) {
-      my_s = __ldg(a.src + row0 + r);
-      my_d = __ldg(a.dst + row0 + r);
-    }
-    const float* vdeg_row = (IS_V && a.vdeg != nullptr) ? a.vdeg + row0 + r : nullptr;
-    k1_cell_tile<HP, IS_V ? 0 : 1, CLAMP, true>(gtile, r, lane, t_acc, &b.acc_full[e], af & 1, nullptr, ln_s, vdeg_row,
-                                                b_s, tl, e, n);
-    ++af;
-    // h' planes are in the slot (first MLP operand) / the accumulator is drained
-    ptx::fence_proxy_async_smem();
-    ptx::tcgen05_fence_before();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive_remote(act_ready_leader);
-    if (nl > 0) {
-      float v[64];
-#pragma unroll 1
-      for (int l = 0; l < NL; ++l) {
-        ptx::mbar_wait(&b.acc_full[e], af & 1);
-        ++af;
-        ptx::tcgen05_fence_after();
-        ptx::tmem_ld64(t_acc, v);
-        const uint32_t bl = bias_s + l * 256;       // broadcast LDS.128: four bias values per load
-        if (l < NL - 1) {
-          // hidden layer feeding the next MMA: bias + ReLU + bf16 split, in place (this layer's MMA has
-          // finished reading the slot: its completion is what acc_full signals)
-          const uint32_t nxt = b_s + r * 16;
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            uint32_t hi[4], lo[4];
-            const float4 ba = ptx::lds128f(bl + ch * 32), bb = ptx::lds128f(bl + ch * 32 + 16);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const int j = ch * 8 + 2 * p;
-              const float2 bp = (p == 0) ? make_float2(ba.x, ba.y) : (p == 1) ? make_float2(ba.z, ba.w)
-                              : (p == 2) ? make_float2(bb.x, bb.y) : make_float2(bb.z, bb.w);
-              const float2 x = ptx::relu2(__fadd2_rn(make_float2(v[j], v[j + 1]), bp));
-              ptx::split_bf16x2_p(x, hi[p], lo[p]);
-            }
-            ptx::sts128(nxt + ch * 2048, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-            if (HP == 2) ptx::sts128(nxt + PLANE_BYTES + ch * 2048, make_uint4(lo[0], lo[1], lo[2], lo[3]));
-          }
-          ptx::fence_proxy_async_smem();
-        } else {
-          // last layer of the chain, kept in fp32: edge tiles bias + ReLU (a3 of the folded MLP),
-          // vertex tiles bias only (linear output layer, graphnn.py:17)
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float4 bb = ptx::lds128f(bl + q * 16);
-            float2 x0 = __fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(bb.x, bb.y));
-            float2 x1 = __fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(bb.z, bb.w));
-            if (!IS_V) {
-              x0 = ptx::relu2(x0);
-              x1 = ptx::relu2(x1);
-            }
-            v[4 * q] = x0.x; v[4 * q + 1] = x0.y; v[4 * q + 2] = x1.x; v[4 * q + 3] = x1.y;
-          }
-        }
-        ptx::tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_remote(act_ready_leader);   // next operand written / accumulator drained
-        tl_mark(tl, e, n, 6);
-      }
-      // stage the fp32 rows in the slot (its last MMA has completed), then every warp walks its own
-      // 32 rows, two rows per instruction (a half-warp covers the 256 bytes of a row)
-      if (!(a.dbg & 2)) {
-#pragma unroll
-      for (int q = 0; q < 16; ++q)
-        ptx::sts128f(b_s + stage_off(r, q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-      __syncwarp();
-      const int64_t g0 = row0 + q4 * 32;
-      const int hw = lane >> 4, c16 = lane & 15;
-      if (IS_V) {
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + hw;
-          if (g0 + rr < n_rows) {
-            const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
-            *reinterpret_cast<float4*>(a.mV_out + (g0 + rr) * D + 4 * c16) = m;
-          }
-        }
-      } else {
-        // dst side: one vector reduction per row; src side accumulated over runs of equal src
-        // (rows of a complete graph are sorted by src, instance_loader.py:60)
-        int cur_s = -1;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + hw;
-          const int s = __shfl_sync(0xffffffffu, my_s, rr);
-          const int d = __shfl_sync(0xffffffffu, my_d, rr);
-          if (s >= 0) {
-            const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
-            if (!(a.dbg & 1)) ptx::red_add_v4(a.xV_out + static_cast<int64_t>(d) * D + 4 * c16, m);
-            if (s != cur_s) {
-              if (cur_s >= 0 && !(a.dbg & 1)) ptx::red_add_v4(a.xV_out + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
-              cur_s = s;
-              acc = m;
-            } else {
-              acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
-            }
-          }
-        }
-        if (cur_s >= 0 && !(a.dbg & 1)) ptx::red_add_v4(a.xV_out + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
-      }
-      }
-    }
-    // every warp of the warpgroup is done with the slot: it becomes the home of tile n + NH
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
-    if (q4 == 0 && lane == 0 && n + NH < ntiles) {
+  uint32_t af = 0;              // acc_full phases consumed by this warpgroup, over the whole launch
+  for (int t = 0; t < geo.n_steps; ++t) {
+    const int nl = (a.dbg & 4) ? 0 : geo.nl(t);
+    long long* tl = (t == 0 && q4 == 0 && lane == 0) ? a.timeline : nullptr;
+    const float* mV_in = a.mVb[t & 1];
+    float* mV_out = a.mVb[(t + 1) & 1];
+    float* xV_in = a.xVb[t & 1];
+    float* xV_out = a.xVb[(t + 1) & 1];
+    const int base = t * ntiles;
+    if (ntiles > 0) {
+      // x operand of the timestep's first tile: built by all eight chain warps, which have nothing
+      // else to do until the first accumulator is ready
+      k1_boot_fill_tile<HP, IS_V, false>(mV_in, xV_in, a.src, a.dst, smem + L::SLOT_OFF, warp - 4, lane, geo.tile(0));
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive_expect_tx(&b.h_full[hs], HP * PLANE_BYTES);
-      ptx::bulk_g2s(smem + L::SLOT_OFF + (1 + hs) * L::SLOT_BYTES,
-                    state + static_cast<int64_t>(2 * (p0 + n + NH) + rank) * tile_bytes(HP), HP * PLANE_BYTES,
-                    &b.h_full[hs]);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(b.boot);
     }
-    tl_mark(tl, e, n, 7);
+    for (int n = (e ^ base) & 1; n < ntiles; n += 2) {
+      const int tile = geo.tile(n);
+      const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
+      const int hs = (base + n) % NH;
+      const uint32_t b_s = slots_s + (1 + hs) * L::SLOT_BYTES;
+      uint8_t* gtile = state + static_cast<int64_t>(tile) * tile_bytes(HP);
+      // endpoints of this warp's 32 rows, fetched a whole chain ahead of the scatter that uses them
+      int my_s = -1, my_d = -1;
+      if (!IS_V && nl > 0 && row0 + r < n_rows) {
+        my_s = __ldg(a.src + row0 + r);
+        my_d = __ldg(a.dst + row0 + r);
+      }
+      const float* vdeg_row = (IS_V && a.vdeg != nullptr) ? a.vdeg + row0 + r : nullptr;
+      k1_cell_tile<HP, IS_V ? 0 : 1, CLAMP, true>(gtile, r, lane, t_acc, &b.acc_full[e], af & 1, nullptr, ln_s, vdeg_row,
+                                                  b_s, tl, e, n);
+      ++af;
+      // h' planes are in the slot (first MLP operand) / the accumulator is drained; they are also in
+      // global memory for the next timestep's bulk copy, an async-proxy read: hence the all-space proxy
+      // fence below
+      ptx::fence_proxy_async_smem();
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote_relaxed(act_ready_leader);
+      ptx::fence_proxy_async_all();      // (global h' planes; off the critical path: the warpgroup waits for the MMA now)
+      if (nl > 0) {
+        float v[64];
+#pragma unroll 1
+        for (int l = 0; l < NL; ++l) {
+          ptx::mbar_wait(&b.acc_full[e], af & 1);
+          ++af;
+          ptx::tcgen05_fence_after();
+          ptx::tmem_ld64(t_acc, v);
+          const uint32_t bl = bias_s + l * 256;       // broadcast LDS.128: four bias values per load
+          if (l < NL - 1) {
+            // hidden layer feeding the next MMA: bias + ReLU + bf16 split, in place (this layer's MMA has
+            // finished reading the slot: its completion is what acc_full signals)
+            const uint32_t nxt = b_s + r * 16;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              uint32_t hi[4], lo[4];
+              const float4 ba = ptx::lds128f(bl + ch * 32), bb = ptx::lds128f(bl + ch * 32 + 16);
+#pragma unroll
+              for (int p = 0; p < 4; ++p) {
+                const int j = ch * 8 + 2 * p;
+                const float2 bp = (p == 0) ? make_float2(ba.x, ba.y) : (p == 1) ? make_float2(ba.z, ba.w)
+                                : (p == 2) ? make_float2(bb.x, bb.y) : make_float2(bb.z, bb.w);
+                const float2 x = ptx::relu2(__fadd2_rn(make_float2(v[j], v[j + 1]), bp));
+                ptx::split_bf16x2_p(x, hi[p], lo[p]);
+              }
+              ptx::sts128(nxt + ch * 2048, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+              if (HP == 2) ptx::sts128(nxt + PLANE_BYTES + ch * 2048, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            }
+            ptx::fence_proxy_async_smem();
+          } else {
+            // last layer of the chain, kept in fp32: edge tiles bias + ReLU (a3 of the folded MLP),
+            // vertex tiles bias only (linear output layer, graphnn.py:17)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 bb = ptx::lds128f(bl + q * 16);
+              float2 x0 = __fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(bb.x, bb.y));
+              float2 x1 = __fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(bb.z, bb.w));
+              if (!IS_V) {
+                x0 = ptx::relu2(x0);
+                x1 = ptx::relu2(x1);
+              }
+              v[4 * q] = x0.x; v[4 * q + 1] = x0.y; v[4 * q + 2] = x1.x; v[4 * q + 3] = x1.y;
+            }
+          }
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_remote_relaxed(act_ready_leader);   // next operand written / accumulator drained
+          tl_mark(tl, e, n, 6);
+        }
+        // stage the fp32 rows in the slot (its last MMA has completed), then every warp walks its own
+        // 32 rows, two rows per instruction (a half-warp covers the 256 bytes of a row)
+        if (!(a.dbg & 2)) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            ptx::sts128f(b_s + stage_off(r, q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          __syncwarp();
+          const int64_t g0 = row0 + q4 * 32;
+          const int hw = lane >> 4, c16 = lane & 15;
+          if (IS_V) {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+              const int rr = 2 * i + hw;
+              if (g0 + rr < n_rows) {
+                const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
+                *reinterpret_cast<float4*>(mV_out + (g0 + rr) * D + 4 * c16) = m;
+              }
+            }
+          } else {
+            // dst side: one vector reduction per row; src side accumulated over runs of equal src
+            // (rows of a complete graph are sorted by src, instance_loader.py:60)
+            const bool red = !(a.dbg & 1);
+            int cur_s = -1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+              const int rr = 2 * i + hw;
+              const int s = __shfl_sync(0xffffffffu, my_s, rr);
+              const int d = __shfl_sync(0xffffffffu, my_d, rr);
+              if (s >= 0) {
+                const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
+                if (red) ptx::red_add_v4(xV_out + static_cast<int64_t>(d) * D + 4 * c16, m);
+                if (s != cur_s) {
+                  if (cur_s >= 0 && red) ptx::red_add_v4(xV_out + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
+                  cur_s = s;
+                  acc = m;
+                } else {
+                  acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
+                }
+              }
+            }
+            if (cur_s >= 0 && red) ptx::red_add_v4(xV_out + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
+          }
+        }
+      }
+      // every warp of the warpgroup is done with the slot: it becomes the home of tile n + NH
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+      if (q4 == 0 && lane == 0 && n + NH < ntiles) {
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive_expect_tx(&b.h_full[hs], HP * PLANE_BYTES);
+        ptx::bulk_g2s(smem + L::SLOT_OFF + (1 + hs) * L::SLOT_BYTES,
+                      state + static_cast<int64_t>(geo.tile(n + NH)) * tile_bytes(HP), HP * PLANE_BYTES, &b.h_full[hs]);
+      }
+      tl_mark(tl, e, n, 7);
+    }
+    if (t + 1 < geo.n_steps) f_grid_sync(a.grid_ctr, static_cast<unsigned int>(t + 1) * geo.nctas);
   }
 }
 
@@ -484,15 +582,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_step_kernel(const FArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::BAR_OFF + 8 * L::NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rank = static_cast<int>(ptx::cluster_ctarank());
   const int cluster = static_cast<int>(blockIdx.x) >> 1, nclusters = static_cast<int>(gridDim.x) >> 1;
   const bool is_v = cluster >= a.e_clusters;
-  int p0, p1;
-  if (is_v) tile_range(cluster - a.e_clusters, nclusters - a.e_clusters, a.pairsV, p0, p1);
-  else tile_range(cluster, a.e_clusters, a.pairsE, p0, p1);
-  const int ntiles = p1 - p0;               // this CTA's tiles: 2 * (p0 + n) + rank
-  uint8_t* state = is_v ? a.stateV : a.stateE;
-  const int nh = is_v ? L::NH_V : L::NH_E;
+  FGeo geo;
+  geo.rank = static_cast<int>(ptx::cluster_ctarank());
+  int p1;
+  if (is_v) tile_range(cluster - a.e_clusters, nclusters - a.e_clusters, a.pairsV, geo.p0, p1);
+  else tile_range(cluster, a.e_clusters, a.pairsE, geo.p0, p1);
+  geo.ntiles = p1 - geo.p0;               // this CTA's tiles: 2 * (p0 + n) + rank
+  geo.nh = is_v ? L::NH_V : L::NH_E;
+  geo.n_steps = a.n_steps;
+  geo.nl_full = is_v ? 4 : 3;
+  geo.skip_last = a.skip_last_mlp;
+  geo.nctas = static_cast<int>(gridDim.x);
   const int tab_off = is_v ? L::TAB_OFF_V : L::TAB_OFF_E;
 
   if (tid == 0) {
@@ -503,16 +605,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_step_kernel(const FArgs a) {
     ptx::mbar_init(&b.act_ready[1], 8);
     ptx::mbar_init(b.boot, 8);
     ptx::fence_mbar_init();
-    if (ntiles > 0) {   // weight images: parameters, not produced by the preceding kernel
-      const int wm_bytes = (is_v ? 4 : 3) * L::WM_LAYER;
-      const uint8_t* wl = (is_v ? a.wlV : a.wlE) + static_cast<int64_t>(rank) * L::WL_BYTES;
-      const uint8_t* wm = (is_v ? a.wmV : a.wmE) + static_cast<int64_t>(rank) * L::WM_BYTES;
-      ptx::mbar_arrive_expect_tx(b.w, L::WL_BYTES + wm_bytes);
-      for (int off = 0; off < L::WL_BYTES; off += 32768) ptx::bulk_g2s(smem + L::WL_OFF + off, wl + off, 32768, b.w);
-      ptx::bulk_g2s(smem + L::WM_OFF, wm, wm_bytes, b.w);
-    }
+    // weight images: parameters, not produced by the preceding kernel
+    const int wm_bytes = (is_v ? 4 : 3) * L::WM_LAYER;
+    const uint8_t* wl = (is_v ? a.wlV : a.wlE) + static_cast<int64_t>(geo.rank) * L::WL_BYTES;
+    const uint8_t* wm = (is_v ? a.wmV : a.wmE) + static_cast<int64_t>(geo.rank) * L::WM_BYTES;
+    ptx::mbar_arrive_expect_tx(b.w, L::WL_BYTES + wm_bytes);
+    for (int off = 0; off < L::WL_BYTES; off += 32768) ptx::bulk_g2s(smem + L::WL_OFF + off, wl + off, 32768, b.w);
+    ptx::bulk_g2s(smem + L::WM_OFF, wm, wm_bytes, b.w);
   }
-  if (warp == 8) ptx::tmem_alloc_pair(tmem_slot, 512);
+  if (warp == 0) ptx::tmem_alloc_pair(tmem_slot, 512);
   {
     // LayerNorm parameters of this CTA's cell as the epilogue wants them (see tc_lnlstm_kernel) and
     // the biases of its message MLP
@@ -536,52 +637,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_step_kernel(const FArgs a) {
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
 
-  if (warp < 8) {
+  if (warp >= 4) {
     ptx::setmaxnreg_inc<200>();
-    if (ntiles > 0) {
-      uint8_t* x0 = smem + L::SLOT_OFF;
-      if (is_v) k1_boot_fill_tile<HP, true>(a.mV_in, a.xV_in, a.src, a.dst, x0, warp, lane, 2 * p0 + rank);
-      else k1_boot_fill_tile<HP, false>(a.mV_in, a.xV_in, a.src, a.dst, x0, warp, lane, 2 * p0 + rank);
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(b.boot);
-    }
     const bool clamp = (is_v ? a.clampV : a.clampE) != 0;
     if (is_v) {
-      if (clamp) f_chain<HP, true, true>(a, smem, b, tmem, p0, rank, ntiles, warp, lane, ln_s, bias_s);
-      else f_chain<HP, true, false>(a, smem, b, tmem, p0, rank, ntiles, warp, lane, ln_s, bias_s);
+      if (clamp) f_chain<HP, true, true>(a, smem, b, tmem, geo, warp, lane, ln_s, bias_s);
+      else f_chain<HP, true, false>(a, smem, b, tmem, geo, warp, lane, ln_s, bias_s);
     } else {
-      if (clamp) f_chain<HP, false, true>(a, smem, b, tmem, p0, rank, ntiles, warp, lane, ln_s, bias_s);
-      else f_chain<HP, false, false>(a, smem, b, tmem, p0, rank, ntiles, warp, lane, ln_s, bias_s);
+      if (clamp) f_chain<HP, false, true>(a, smem, b, tmem, geo, warp, lane, ln_s, bias_s);
+      else f_chain<HP, false, false>(a, smem, b, tmem, geo, warp, lane, ln_s, bias_s);
     }
   } else {
     ptx::setmaxnreg_dec<104>();
-    if (warp == 8) {
-      if (ntiles > 0) {
-        const int nl = a.skip_mlp ? 0 : (is_v ? 4 : 3);
-        if (rank == 0) f_mma<HP>(smem, b, tmem, ntiles, nl, nh, a.timeline);
-        else f_forward(b, ntiles, nh);
-      }
+    if (warp == 0) {
+      if (geo.rank == 0) f_mma<HP>(a, smem, b, tmem, geo);
+      else f_forward(a, b, geo);
     } else {
-      if (warp == 9 && lane == 0) {
-        // h planes of the first tiles; later ones are fetched by the warpgroup that retires a slot
-        for (int n = 0; n < ntiles && n < nh; ++n) {
-          ptx::mbar_arrive_expect_tx(&b.h_full[n], HP * PLANE_BYTES);
-          ptx::bulk_g2s(smem + L::SLOT_OFF + (1 + n) * L::SLOT_BYTES,
-                        state + static_cast<int64_t>(2 * (p0 + n) + rank) * tile_bytes(HP), HP * PLANE_BYTES,
-                        &b.h_full[n]);
-        }
-      }
-      __syncwarp();
-      if (is_v) f_producer<HP, true>(a, smem + L::SLOT_OFF, b, p0, rank, ntiles, warp - 9, lane);
-      else f_producer<HP, false>(a, smem + L::SLOT_OFF, b, p0, rank, ntiles, warp - 9, lane);
+      if (is_v) f_producer<HP, true>(a, smem, b, geo, warp - 1, lane);
+      else f_producer<HP, false>(a, smem, b, geo, warp - 1, lane);
     }
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
   // the peer's shared memory and TMEM must stay alive until every MMA of the pair has completed
   ptx::cluster_sync();
-  if (warp == 8) ptx::tmem_dealloc_pair(tmem, 512);
+  if (warp == 0) ptx::tmem_dealloc_pair(tmem, 512);
 }
 
 }  // namespace tspgnn

@@ -86,6 +86,7 @@ struct K2Args {
   // W4 (merged into its LSTM kernel) once per vertex instead of once per edge (K1Args::vdeg).
   int fold;
   const float* bias_tab;   // [3 MLPs][4][64] biases (V_msg_E, E_msg_V, E_vote), coalesced copy for the prologue
+  unsigned int* zero_word; // optional: cleared by this launch (grid barrier counter of the persistent kernel that follows)
   long long* timeline;
 };
 
@@ -134,9 +135,11 @@ static_assert(K1Smem<2>::DYN_BYTES <= 232448, "K1 shared memory budget (227 KB)"
 // E rows: x = mV[src] + mV[dst] (= EV . msg, model.py:85-91); V rows: x = xV (then cleared).
 // A warp instruction covers 8 rows x 4 chunks: lane -> (row r8 = lane & 7, chunk cq = lane >> 3),
 // so every quarter-warp writes 128 contiguous bytes of shared memory (no bank conflicts).
-template <int HP, bool IS_V>
-__device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64_t row0, const float* __restrict__ mV,
-                                          float* __restrict__ xV, const int (&si)[6], const int (&di)[6]) {
+// NC = true: the messages are read through the non-coherent path (legal when a previous LAUNCH wrote them);
+// false: coherent loads, for the persistent kernel whose messages are written during the same launch.
+template <int HP, bool IS_V, bool NC = true>
+__device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64_t row0, const float* mV,
+                                          float* xV, const int (&si)[6], const int (&di)[6]) {
   const int r8 = lane & 7, cq = lane >> 3;
   const uint32_t slot_s = ptx::smem_u32(slot);
 #pragma unroll
@@ -157,8 +160,13 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
           x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
         } else {
           float u[8], w[8];
-          ptx::ldg256(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u);
-          ptx::ldg256(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w);
+          if (NC) {
+            ptx::ldg256(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u);
+            ptx::ldg256(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w);
+          } else {
+            ptx::ldg256_coherent(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u);
+            ptx::ldg256_coherent(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) x[i] = u[i] + w[i];
         }
@@ -175,8 +183,8 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
 // The x operand of a CTA's FIRST tile is built by the eight epilogue warps, which have nothing to do
 // until the first accumulator is ready and have the registers to keep every load in flight: the
 // first gather drops from three L2 round trips to one and the gather warps start on tile 1 at once.
-template <int HP, bool IS_V>
-__device__ __forceinline__ void k1_boot_fill_tile(const float* __restrict__ mV, float* __restrict__ xV,
+template <int HP, bool IS_V, bool NC = true>
+__device__ __forceinline__ void k1_boot_fill_tile(const float* mV, float* xV,
                                                   const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                                   uint8_t* slot, int warp, int lane, int tile) {
   struct { const float* mV; float* xV; const int32_t* src; const int32_t* dst; } a = {mV, xV, src, dst};
@@ -207,8 +215,13 @@ __device__ __forceinline__ void k1_boot_fill_tile(const float* __restrict__ mV, 
         x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
       } else {
         float u[8], w[8];
-        ptx::ldg256(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8, u);
-        ptx::ldg256(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8, w);
+        if (NC) {
+          ptx::ldg256(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8, u);
+          ptx::ldg256(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8, w);
+        } else {
+          ptx::ldg256_coherent(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8, u);
+          ptx::ldg256_coherent(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8, w);
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = u[i] + w[i];
       }
@@ -957,6 +970,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   const uint32_t bias_s = ptx::smem_u32(smem + L::BIAS_OFF);
   ptx::grid_dependency_wait();       // prologue above overlaps the previous kernel's tail
   ptx::grid_launch_dependents();
+  if (a.zero_word != nullptr && blockIdx.x == 0 && tid == 0) *a.zero_word = 0u;
 
   if (warp < 4 * K2_CHAINS) {
     if (a.vote_mode) k2_chain<HP, 2>(a, slots, acc_full, act_ready, slot_free, tmem, t0, ntiles, warp, lane, bias_s);

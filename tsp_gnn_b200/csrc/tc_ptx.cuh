@@ -50,6 +50,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// same for every state space: also orders this thread's global stores before later async-proxy reads
+// of them (the bulk copies that fetch the h planes of the next timestep in the persistent kernel)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -156,6 +159,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
 // the thread (the 48 KB of state a chain warpgroup has just written) before the barrier is signalled.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Same without release semantics.  The chain warps signal "operand written / accumulator drained":
+// the operand is shared memory already made visible to the async proxy by a preceding
+// fence.proxy.async (which completes before the arrive issues), the accumulator reads are ordered by
+// tcgen05.fence::before_thread_sync; the release form would add a MEMBAR that also waits for the 48 KB
+// of global state stores a warpgroup has in flight at that point.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // non-blocking test of a local barrier
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
@@ -381,6 +392,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
+// coherent variant (the data may have been written by other SMs earlier in the same launch)
+__device__ __forceinline__ void ldg256_coherent(const float* p, float (&f)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+               : "l"(p)
+               : "memory");
+}
 // 32-byte read-only global load (LDG.E.256, sm_100): one request per 32-byte sector instead of two
 // 16-byte loads that each fetch it
 __device__ __forceinline__ void ldg256(const float* p, float (&f)[8]) {

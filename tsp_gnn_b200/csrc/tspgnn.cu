@@ -144,7 +144,9 @@ struct tspgnn_ctx {
   uint8_t* d_wl_pair[2] = {nullptr, nullptr};         // [0] folded V cell, [1] E cell: [rank][plane][kblock] x 16 KB
   uint8_t* d_wm_pair[2] = {nullptr, nullptr};         // [0] V_msg_E, [1] E_msg_V:      [rank][layer][plane] x 4 KB
   float *mV2 = nullptr, *xV2 = nullptr;               // second halves of the message double buffers
-  bool fused = false;                                 // tspgnn_step uses the fused kernel (tensor-core modes)
+  unsigned int* d_gridctr = nullptr;                  // grid barrier counter of the persistent fused kernel
+  bool fused = false;                                 // tspgnn_step uses the persistent fused kernel (tensor-core modes);
+                                                      // off by default: 6-10 % slower than the two-kernel sequence so far
   int dbg = 0;                                        // measurement aid of the fused kernel (FArgs::dbg; 4 = never any messages)
   double v_pair_weight = 1.3;                         // cost of a vertex tile pair relative to an edge tile pair
   // plan
@@ -257,6 +259,13 @@ extern "C" int tspgnn_create(int d, int mode, int device, tspgnn_handle* out) {
   CUDA_TRY(cudaFuncSetAttribute(tc_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Smem<2>::DYN_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tc_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<1>::DYN_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(tc_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FSmem<2>::DYN_BYTES));
+  if (h->hp > 0) {
+    if (dev_alloc(&h->d_gridctr, 1)) {
+      delete h;
+      return TSPGNN_E_CUDA;
+    }
+    CUDA_TRY(cudaMemset(h->d_gridctr, 0, sizeof(unsigned int)));
+  }
   *out = h;
   return 0;
 }
@@ -275,7 +284,7 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
     for (void* p : wp)
       if (p) cudaFree(p);
   }
-  void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2};
+  void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2, h->d_gridctr};
   for (void* p : fp)
     if (p) cudaFree(p);
   void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg, h->d_lntab, h->d_biastab};
@@ -714,6 +723,7 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, lon
   a.timeline = timeline;
   a.fold = (fold && !vote) ? 1 : 0;
   a.bias_tab = h->d_biastab;
+  a.zero_word = h->d_gridctr;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = vote ? h->d_wmlp[2] : h->d_wmlp[1];
@@ -762,10 +772,11 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, bool fold, long long* tim
   return 0;
 }
 
-// One fused timestep on CTA pairs (tc_fused.cuh).  `phase` selects which halves of the message double
-// buffers are read (phase & 1) and written; `skip_mlp` = last timestep of a call.
+// `n_steps` fused timesteps on CTA pairs in ONE persistent launch (tc_fused.cuh).  Timestep t reads the
+// halves t & 1 of the message double buffers (the message kernel launched before filled halves 0) and
+// writes the other ones; `skip_last` = nobody consumes the messages of the final state.
 template <int HP>
-static int tc_launch_fused(tspgnn_ctx* h, cudaStream_t s, int phase, bool skip_mlp, long long* timeline = nullptr) {
+static int tc_launch_fused(tspgnn_ctx* h, cudaStream_t s, int n_steps, bool skip_last, long long* timeline = nullptr) {
   FArgs a;
   a.timeline = timeline;
   a.stateE = h->stateE;
@@ -774,12 +785,10 @@ static int tc_launch_fused(tspgnn_ctx* h, cudaStream_t s, int phase, bool skip_m
   a.wlV = h->d_wl_pair[0];
   a.wmE = h->d_wm_pair[1];
   a.wmV = h->d_wm_pair[0];
-  float* mVb[2] = {h->mV, h->mV2};
-  float* xVb[2] = {h->xV, h->xV2};
-  a.mV_in = mVb[phase & 1];
-  a.mV_out = mVb[(phase + 1) & 1];
-  a.xV_in = xVb[phase & 1];
-  a.xV_out = xVb[(phase + 1) & 1];
+  a.mVb[0] = h->mV;
+  a.mVb[1] = h->mV2;
+  a.xVb[0] = h->xV;
+  a.xVb[1] = h->xV2;
   a.src = h->d_src;
   a.dst = h->d_dst;
   a.nE = h->nE;
@@ -788,13 +797,16 @@ static int tc_launch_fused(tspgnn_ctx* h, cudaStream_t s, int phase, bool skip_m
   a.pairsV = h->tilesV / 2;
   a.clampV = h->clamp_cell[0];
   a.clampE = h->clamp_cell[1];
-  a.skip_mlp = (skip_mlp || (h->dbg & 4)) ? 1 : 0;
+  a.n_steps = n_steps;
+  a.skip_last_mlp = skip_last ? 1 : 0;
   a.dbg = h->dbg;
+  a.grid_ctr = h->d_gridctr;
   a.vdeg = h->d_deg;
   a.ln_tab = h->d_lntab;
   a.bias_tab = h->d_biastab;
   // clusters are dedicated to edge or to vertex tile pairs; a vertex tile costs about 1.3 edge tiles
-  // (four MLP layers and the degree-bias pass against three layers and the scatter)
+  // (four MLP layers and the degree-bias pass against three layers and the scatter).  Every CTA must be
+  // resident (grid barrier between timesteps): at most one CTA per SM.
   const int max_clusters = h->num_sms / 2;
   int nclusters = std::min(max_clusters, a.pairsE + a.pairsV);
   int ec = static_cast<int>(std::lround(static_cast<double>(nclusters) * a.pairsE / (a.pairsE + h->v_pair_weight * a.pairsV)));
@@ -876,26 +888,22 @@ static int one_step(tspgnn_ctx* h, cudaStream_t s) {
 
 static bool use_fused(const tspgnn_ctx* h) { return h->hp > 0 && h->fused && h->fold; }
 
-// n_steps iterations of while_body.  Tensor-core modes: one message launch for the current state, then
-// one fused launch per timestep (cell -> messages of the new state), the last one without messages;
-// both message double buffers are all-zero (xV) / dead (mV) again when the sequence ends.
+// n_steps iterations of while_body.  Tensor-core modes: one message launch for the current state, then ONE
+// persistent fused launch that runs every timestep (cell -> messages of the new state, grid barrier), the
+// last timestep without messages; both message double buffers are all-zero (xV) / dead (mV) again at the end.
 static int run_steps(tspgnn_ctx* h, cudaStream_t s, int n_steps) {
   if (!use_fused(h)) {
     for (int t = 0; t < n_steps; ++t)
       if (one_step(h, s)) return TSPGNN_E_CUDA;
     return 0;
   }
-  if (step_messages(h, s, true)) return TSPGNN_E_CUDA;
-  for (int t = 0; t < n_steps; ++t) {
-    const int rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, t, t == n_steps - 1) : tc_launch_fused<1>(h, s, t, t == n_steps - 1);
-    if (rc) return rc;
-  }
-  return 0;
+  if (step_messages(h, s, true)) return TSPGNN_E_CUDA;      // also clears the grid barrier counter
+  return (h->hp == 2) ? tc_launch_fused<2>(h, s, n_steps, true) : tc_launch_fused<1>(h, s, n_steps, true);
 }
 
 static int64_t launches_per_call(const tspgnn_ctx* h, int n_steps) {
   if (h->hp == 0) return static_cast<int64_t>(n_steps) * 5;
-  return use_fused(h) ? n_steps + 1 : static_cast<int64_t>(n_steps) * 2;
+  return use_fused(h) ? 2 : static_cast<int64_t>(n_steps) * 2;
 }
 
 extern "C" int tspgnn_init_embeddings(tspgnn_handle h, const float* dW, const float* dC, void* stream) {
@@ -942,7 +950,12 @@ extern "C" int tspgnn_step(tspgnn_handle h, int n_steps, void* stream) {
   if (n_steps == 0) return 0;
   // The per-step launch sequence is identical every timestep: capture it once per
   // (plan, n_steps) into a CUDA graph and replay it.  Legacy default stream cannot capture.
-  if (s == nullptr || n_steps < 2) return run_steps(h, s, n_steps);
+  if (s == nullptr || n_steps < 2 || use_fused(h)) return [&]() {      // two launches: nothing for a graph to save
+    const int64_t before = h->launches;
+    const int rc = run_steps(h, s, n_steps);
+    h->launches = before + launches_per_call(h, n_steps);
+    return rc;
+  }();
   auto it = h->step_graphs.find(n_steps);
   if (it == h->step_graphs.end()) {
     cudaGraph_t graph = nullptr;
@@ -1075,22 +1088,19 @@ extern "C" int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* 
   CUDA_TRY(cudaEventCreate(&e1));
   double total = 0.0;
   if (which == 2) {
-    // the fused timestep kernel: messages of the current state first, then `iters` timed launches
-    // that alternate the message double buffers, then one launch without messages (buffers clean again)
+    // the fused timestep kernel: messages of the current state first, then ONE persistent launch of `iters`
+    // timesteps (the last one without messages: buffers clean again); the mean is per timestep
     if (step_messages(h, s, true)) return TSPGNN_E_CUDA;
-    for (int i = 0; i <= iters; ++i) {
-      CUDA_TRY(cudaEventRecord(e0, s));
-      const int rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, i, i == iters) : tc_launch_fused<1>(h, s, i, i == iters);
-      if (rc) return rc;
-      CUDA_TRY(cudaEventRecord(e1, s));
-      CUDA_TRY(cudaEventSynchronize(e1));
-      float ms = 0.f;
-      CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-      if (i < iters) total += ms;
-    }
+    CUDA_TRY(cudaEventRecord(e0, s));
+    const int rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, iters, true) : tc_launch_fused<1>(h, s, iters, true);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    *mean_ms = static_cast<float>(total / iters);
+    *mean_ms = ms / iters;
     return 0;
   }
   for (int i = 0; i < iters; ++i) {
@@ -1138,8 +1148,7 @@ extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_
   if (which == 2) {
     // fused timestep kernel: messages, one traced launch, one launch without messages (buffers clean again)
     rc = step_messages(h, s, true);
-    if (!rc) rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, 0, false, d) : tc_launch_fused<1>(h, s, 0, false, d);
-    if (!rc) rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, 1, true) : tc_launch_fused<1>(h, s, 1, true);
+    if (!rc) rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, 2, true, d) : tc_launch_fused<1>(h, s, 2, true, d);
   } else if (which == 0) {
     rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold) : tc_launch_k2<1>(h, s, false, h->fold);
     if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold, d) : tc_launch_k1<1>(h, s, h->fold, d);
