@@ -155,6 +155,27 @@ int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* mean_ms, vo
  * warp roles, copied to out_host[cta][role][tile][event] (148*4*64*8 int64). */
 int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_host, int64_t n_int64, void* stream);
 
+/* ---- generic building blocks (stateless; fp32 row-major device pointers on `device`, asynchronous on `stream`) ----
+ * They execute the parts of the reference's public surface that the fused TSP kernels do not cover:
+ * stand-alone Mlp evaluation and GraphNN topologies other than build_network's (a transfer function, matrix-only
+ * inputs, several update terms per variable; graphnn.py:142-173).  Activation codes: 0 none, 1 relu, 2 tanh, 3 sigmoid.
+ *
+ * tspgnn_dense_forward  : one tf.layers.Dense call (mlp.py:39-52,57-63): Y[rows,out] = act(X[rows,in] . W[in,out] + b);
+ *                         dB may be NULL (use_bias=False).
+ * tspgnn_matmul_coo     : tf.matmul(adjacency, y, adjoint_a=transpose) (graphnn.py:155-161) for a matrix given by its
+ *                         stored entries (row, col, value; d_val NULL = all ones): dOut[out_rows, d] is overwritten.
+ * tspgnn_lnlstm_forward : one LayerNormBasicLSTMCell call (graphnn.py:107-112,167-170) with input width in_dim and
+ *                         `units` units: dXH = [x, h] concatenated [rows, in_dim + units], kernel [(in_dim+units), 4 units],
+ *                         gamma / beta [5][units] in gate order input, transform, forget, output, state;
+ *                         d_scratch holds rows * 4 * units floats. */
+int tspgnn_dense_forward(int device, const float* dX, int64_t rows, int in_dim, const float* dW, const float* dB,
+                         int out_dim, int activation, float* dY, void* stream);
+int tspgnn_matmul_coo(int device, const int32_t* d_row, const int32_t* d_col, const float* d_val, int64_t nnz,
+                      int transpose, const float* dY, int d, int64_t out_rows, float* dOut, void* stream);
+int tspgnn_lnlstm_forward(int device, const float* dXH, int in_dim, const float* dC, int64_t rows, int units,
+                          const float* dKernel, const float* dGamma, const float* dBeta, int activation,
+                          float forget_bias, float* dC_out, float* dH_out, float* d_scratch, void* stream);
+
 /* Host helper: dense EV (row-major [rows, cols], float64 or float32 by elem_size 8/4) ->
  * edge_src/edge_dst (instance_loader.py:63-66 layout).  Returns TSPGNN_E_INVALID if a row
  * does not have exactly two non-zeros. */

@@ -120,6 +120,59 @@ def test_fused_and_two_kernel_timesteps_agree(mode):
         assert state_err(a, b) <= tol, state_err(a, b)
 
 
+# BASELINE config 3 (bf16 embeddings / fp32 accumulate): the error of the recurrent state grows with the number
+# of timesteps and then saturates (LayerNorm keeps the states bounded).  Gates = about 2x the values measured
+# on B200 with reference initialisers on 16 x n=20 (E_h: 4e-3, 9e-3, 1.6e-2, 2.2e-2, 3.0e-2 at T = 1, 2, 4, 8, 32).
+BF16_STATE_GATE = {1: 1.0e-2, 2: 2.0e-2, 4: 3.5e-2, 8: 5.0e-2, 32: 7.0e-2}
+
+
+def test_bf16_mode_state_error_per_timestep_count():
+    EV, W, C, y, nv, ne = inst.synth_batch([20] * 16, seed=42)
+    params = orc.init_params(64, seed=0)
+    report = {}
+    for T, gate in sorted(BF16_STATE_GATE.items()):
+        got = run_engine("bf16", params, EV, W, C, nv, ne, T)
+        ref = orc.forward(params, EV.src, EV.dst, W, C, nv, ne, T, dtype=np.float64)
+        err = {k: state_err(got[k], ref[k]) for k in ("E_h", "E_c", "V_h", "V_c")}
+        errp = float(np.abs(got["predictions"] - ref["predictions"]).max())
+        report[T] = (errp, err)
+        print("bf16 T=%d pred err %.2e" % (T, errp), {k: "%.1e" % v for k, v in err.items()})
+        assert max(err.values()) <= gate, (T, err)
+        assert errp <= TOL_PRED["bf16"], (T, errp)
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_message_kernel_slot_reuse_is_race_free_under_stress(mode):
+    """compute-sanitizer racecheck flags the in-place slot reuse of the message kernel (hidden activations, then the
+    fp32 staging, written by different threads of a chain; ordered through mbarriers the tool does not model).
+    Stress: the same timestep from the same state, many times; the edge states depend only on the vertex messages
+    (plain stores, no atomics) and must be bit-identical every time, the vertex states (atomic scatter order) equal
+    to rounding.  A write-after-write race on the slot would show up as a sporadic bit difference."""
+    import torch
+    rng = np.random.RandomState(5)
+    EV, W, C, y, nv, ne = inst.synth_batch(inst.mixed_sizes(48, 12, 40, seed=9), seed=21)
+    params = orc.init_params(64, seed=6, perturb_ln=True)
+    nV, nE = int(nv.sum()), int(ne.sum())
+    Vh = np.abs(rng.normal(size=(nV, 64))).astype(np.float32); Vc = rng.normal(size=(nV, 64)).astype(np.float32)
+    Eh = np.abs(rng.normal(size=(nE, 64))).astype(np.float32); Ec = rng.normal(size=(nE, 64)).astype(np.float32)
+    eng = make_engine(mode, params)
+    eng.plan(nv, ne, EV.src, EV.dst)
+    t = lambda a: torch.from_numpy(a).cuda()
+    dVh, dVc, dEh, dEc = t(Vh), t(Vc), t(Eh), t(Ec)
+    first = None
+    for rep in range(300):
+        eng.set_states(Vh=dVh, Vc=dVc, Eh=dEh, Ec=dEc)
+        eng.step(1)
+        st = eng.get_states()
+        cur = (st["E"][1].clone(), st["E"][0].clone(), st["V"][1].clone())
+        if first is None:
+            first = cur
+            continue
+        assert torch.equal(cur[0], first[0]) and torch.equal(cur[1], first[1]), "edge states differ in repeat %d" % rep
+        assert float((cur[2] - first[2]).abs().max()) <= 1e-5, rep
+    eng.close()
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_single_timestep_from_random_state(mode):
     """One while_body iteration (graphnn.py:142-173) from arbitrary (c,h): isolates the step kernels."""

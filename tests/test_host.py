@@ -75,15 +75,30 @@ def test_graphnn_check_model_messages():
         tg.GraphNN(var, mat, dict(msg, V_msg_E=("V", "Z")), loop)
 
 
-def test_graphnn_rejects_unsupported_topologies_loudly():
+def test_graphnn_other_topologies_take_the_generic_path():
+    """Only the TSP wiring maps onto the fused kernels; everything else is executed op by op on the generic CUDA
+    building blocks (graphnn.py:142-173) -- never rejected, never a CPU path."""
     var, mat, msg, loop = _tsp_args()
-    with pytest.raises(NotImplementedError):
-        tg.GraphNN(var, mat, msg, loop, MLP_depth=2)
-    with pytest.raises(NotImplementedError):
-        tg.GraphNN({"V": 32, "E": 32}, mat, msg, loop)
+    assert tg.GraphNN(var, mat, msg, loop)._kernel_roles is not None
+    assert tg.GraphNN(var, mat, msg, loop, MLP_depth=2)._kernel_roles is None
+    assert tg.GraphNN({"V": 32, "E": 32}, mat, msg, loop)._kernel_roles is None
     loop2 = dict(loop, V=[{"mat": "EV", "msg": "E_msg_V", "var": "E"}])     # missing transpose
-    with pytest.raises(NotImplementedError):
-        tg.GraphNN(var, mat, msg, loop2)
+    assert tg.GraphNN(var, mat, msg, loop2)._kernel_roles is None
+    # a model with a transfer function, a matrix-only input of integer width and two terms per variable
+    g = tg.GraphNN({"A": 8, "B": 16, "C": 8}, {"M_AB": ("A", "B"), "M_CB": ("C", "B"), "F_C": ("C", 4)},
+                   {"B2A": ("B", "A"), "A2B": ("A", "B"), "B2C": ("B", "C")},
+                   {"A": [{"mat": "M_AB", "msg": "B2A", "var": "B"}, {"var": "A", "fun": lambda y: y * y}],
+                    "B": [{"mat": "M_AB", "transpose?": True, "msg": "A2B", "var": "A"}],
+                    "C": [{"mat": "M_CB", "msg": "B2C", "var": "B"}, {"mat": "F_C"}]}, name="TOY")
+    assert g._kernel_roles is None
+    assert (g.input_width("A"), g.input_width("B"), g.input_width("C")) == (16, 16, 12)
+    p = g.init_parameters(seed=1)
+    assert sorted(p) == sorted(g.variable_names())
+    assert p["TOY/A_cell/layer_norm_basic_lstm_cell/kernel"].shape == (24, 32)
+    assert p["TOY/C_cell/layer_norm_basic_lstm_cell/kernel"].shape == (20, 32)
+    assert p["TOY/B2A_MLP_layer_4/kernel"].shape == (16, 8) and p["TOY/B2A_MLP_layer_4/bias"].shape == (8,)
+    with pytest.raises(RuntimeError, match="uninitialized"):
+        tg.Mlp([4, 4], name="m")(np.zeros((2, 3), dtype=np.float32))
 
 
 def test_graphnn_check_run_shapes():

@@ -17,6 +17,7 @@
 #include "tc_kernels.cuh"
 #include "tc_fused.cuh"
 #include "train_kernels.cuh"
+#include "generic_kernels.cuh"
 
 using namespace tspgnn;
 
@@ -1196,6 +1197,58 @@ extern "C" int tspgnn_dense_ev_to_coo(const void* EV, int elem_size, int64_t row
     edge_src[e] = c2[0];
     edge_dst[e] = c2[1];
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// generic building blocks (stateless; device pointers on `device`)
+// ------------------------------------------------------------------------------------
+extern "C" int tspgnn_dense_forward(int device, const float* dX, int64_t rows, int in_dim, const float* dW,
+                                    const float* dB, int out_dim, int activation, float* dY, void* stream) {
+  if (!dX || !dW || !dY) return fail(TSPGNN_E_INVALID, "NULL argument");
+  if (rows < 0 || in_dim <= 0 || out_dim <= 0 || activation < 0 || activation > 3)
+    return fail(TSPGNN_E_INVALID, "bad shape or activation code (rows=%lld in=%d out=%d act=%d)", (long long)rows, in_dim,
+                out_dim, activation);
+  if (rows == 0) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  const dim3 grid(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((out_dim + 63) / 64));
+  generic_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dX, rows, in_dim, dW, dB, out_dim, activation, dY);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tspgnn_matmul_coo(int device, const int32_t* d_row, const int32_t* d_col, const float* d_val, int64_t nnz,
+                                 int transpose, const float* dY, int d, int64_t out_rows, float* dOut, void* stream) {
+  if (!dY || !dOut || (nnz > 0 && (!d_row || !d_col))) return fail(TSPGNN_E_INVALID, "NULL argument");
+  if (nnz < 0 || d <= 0 || out_rows < 0) return fail(TSPGNN_E_INVALID, "bad sizes");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(dOut, 0, out_rows * d * sizeof(float), s));
+  if (nnz == 0) return 0;
+  // M . y gathers rows of y by column index and adds into the entry's row; M^T . y the other way round
+  const int32_t* r_out = transpose ? d_col : d_row;
+  const int32_t* r_in = transpose ? d_row : d_col;
+  generic_coo_matmul_kernel<<<static_cast<unsigned>((nnz * d + 255) / 256), 256, 0, s>>>(r_out, r_in, d_val, nnz, d, dY, dOut);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tspgnn_lnlstm_forward(int device, const float* dXH, int in_dim, const float* dC, int64_t rows, int units,
+                                     const float* dKernel, const float* dGamma, const float* dBeta, int activation,
+                                     float forget_bias, float* dC_out, float* dH_out, float* d_scratch, void* stream) {
+  if (!dXH || !dC || !dKernel || !dGamma || !dBeta || !dC_out || !dH_out || !d_scratch)
+    return fail(TSPGNN_E_INVALID, "NULL argument");
+  if (rows < 0 || in_dim <= 0 || units <= 0 || activation < 0 || activation > 3) return fail(TSPGNN_E_INVALID, "bad sizes");
+  if (rows == 0) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // z = [x, h] . kernel (no bias when the gates are layer-normalised)
+  const dim3 grid(static_cast<unsigned>((rows + 63) / 64), static_cast<unsigned>((4 * units + 63) / 64));
+  generic_dense_kernel<<<grid, 256, 0, s>>>(dXH, rows, in_dim + units, dKernel, nullptr, 4 * units, 0, d_scratch);
+  CUDA_TRY(cudaGetLastError());
+  generic_lnlstm_gates_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, s>>>(
+      d_scratch, dC, rows, units, dGamma, dBeta, activation, forget_bias, dC_out, dH_out);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

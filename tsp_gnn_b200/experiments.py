@@ -55,7 +55,17 @@ def get_accuracy(sess, model, batch, time_steps):
     return float(np.mean(sess.run(model["acc"], feed_dict=feed)))
 
 
-def accuracy_sweep(sess, model, loaders, devs, time_steps, batch_size=16, n_batches=64):
+def get_accuracy_tp(sess, model, batch, time_steps):
+    """experiments/test_varying_dev.py:21-38: that script fetches ``TP`` and divides by the batch size
+    (so it reports the share of instances that are positive AND predicted right, at most 0.5 for the
+    reference's half-positive batches) instead of ``acc``."""
+    EV, W, C, route_exists, n_vertices, n_edges = batch
+    feed = {model["EV"]: EV, model["W"]: W, model["C"]: C, model["time_steps"]: time_steps,
+            model["route_exists"]: route_exists, model["n_vertices"]: n_vertices, model["n_edges"]: n_edges}
+    return float(np.mean(sess.run(model["TP"], feed_dict=feed) / len(n_vertices)))
+
+
+def accuracy_sweep(sess, model, loaders, devs, time_steps, batch_size=16, n_batches=64, metric="acc"):
     """The sweeps behind figures/test_varying_sizes.png and test_varying_dev.png
     (test_varying_sizes.py:82-113, test_varying_dev.py:81-96): mean accuracy over ``n_batches`` batches
     for every (key, deviation).  ``loaders`` maps a key (e.g. the instance size n) to an InstanceLoader.
@@ -64,7 +74,8 @@ def accuracy_sweep(sess, model, loaders, devs, time_steps, batch_size=16, n_batc
     for key, loader in loaders.items():
         for dev in devs:
             loader.reset()
-            accs = [get_accuracy(sess, model, batch, time_steps)
+            fn = get_accuracy_tp if metric == "TP" else get_accuracy     # "TP": test_varying_dev.py's variant
+            accs = [fn(sess, model, batch, time_steps)
                     for batch in islice(loader.get_batches(batch_size, dev), n_batches)]
             out[(key, dev)] = float(np.mean(accs)) if accs else float("nan")
     return out

@@ -5,8 +5,10 @@ time consistency checks (``check_model``, graphnn.py:72-103) and the run-time sh
 (``check_run``, graphnn.py:185-271) with the reference's messages.  Execution is mapped onto
 the fused CUDA timestep kernels, which implement the topology ``build_network`` declares
 (model.py:57-94): two variables, one incidence matrix used plain and transposed, one
-message MLP per direction, one LayerNorm-LSTM update per variable.  Any other topology is
-rejected loudly -- there is no generic fallback path.
+message MLP per direction, one LayerNorm-LSTM update per variable.  Any other topology
+(transfer functions, matrix-only inputs, several update terms per variable, other sizes,
+graphnn.py:142-173) runs update by update on the generic CUDA building blocks of
+tsp_gnn_b200/generic.py -- same semantics, one kernel per op, never a CPU path.
 """
 import collections
 import numpy as np
@@ -32,7 +34,12 @@ class GraphNN(object):
         self.check_model()
         self._init_parameters()
         self._engine = None
-        self._kernel_roles = self._match_fused_topology()
+        try:
+            self._kernel_roles = self._match_fused_topology()
+        except NotImplementedError:
+            self._kernel_roles = None          # executed on the generic building blocks
+        self._generic_params = None
+        self._generic_device = {}
 
     # graphnn.py:72-103 -------------------------------------------------------------
     def check_model(self):
@@ -151,17 +158,117 @@ class GraphNN(object):
         self._engine = engine
         return self
 
-    def __call__(self, adjacency_matrices, initial_embeddings, time_steps, LSTM_initial_states={}):
-        """Runs ``time_steps`` message-passing iterations on the bound engine.
+    # -- generic execution (any topology) ----------------------------------------------------------------
+    def input_width(self, v):
+        """Width of the concatenated cell input of variable v (graphnn.py:146-167)."""
+        w = 0
+        for u in self.loop[v]:
+            if "var" in u:
+                w += self.var[self.msg[u["msg"]][1]] if "msg" in u else self.var[u["var"]]
+            else:
+                second = self.mat[u["mat"]][1]
+                w += second if type(second) is int else self.var[second]
+        return w
 
-        adjacency_matrices[mat] is only shape-checked here (the engine's plan holds the
-        incidence structure); initial_embeddings / LSTM_initial_states are row-major fp32
-        CUDA tensors [N_var, d].  Returns {var: LSTMStateTuple(c, h)} of CUDA tensors.
-        """
-        if self._engine is None:
-            raise RuntimeError("GraphNN is not bound to an engine; use build_network()/Session or GraphNN.bind")
+    def init_parameters(self, seed=0):
+        """Variables of the generic path under the reference's initialisers: message MLP kernels AND biases
+        xavier-uniform (graphnn.py:120-121), LSTM kernels glorot-uniform, LayerNorm gamma 1 / beta 0.
+        Returns {TF variable name: array}; names as variable_names()."""
+        rng = np.random.RandomState(seed)
+        params = {}
+        for msg, (vin, vout) in self.msg.items():
+            for k, a in self._msg_MLPs[msg].init_parameters(self.var[vin], rng).items():
+                params["%s/%s" % (self.name, k)] = a
+        for v, d in self.var.items():
+            base = "{}/{}_cell/layer_norm_basic_lstm_cell".format(self.name, v)
+            fan_in, fan_out = self.input_width(v) + d, 4 * d
+            lim = np.sqrt(6.0 / (fan_in + fan_out))
+            params[base + "/kernel"] = rng.uniform(-lim, lim, size=(fan_in, fan_out)).astype(np.float32)
+            for g in ("input", "transform", "forget", "output", "state"):
+                params["{}/{}/gamma".format(base, g)] = np.ones(d, dtype=np.float32)
+                params["{}/{}/beta".format(base, g)] = np.zeros(d, dtype=np.float32)
+        self.set_parameters(params)
+        return params
+
+    def set_parameters(self, params):
+        """``params``: {TF variable name: array} for every name of variable_names()."""
+        missing = [n for n in self.variable_names() if n not in params]
+        if missing:
+            raise KeyError("missing variables: %r" % (missing[:4],))
+        self._generic_params = {k: np.asarray(params[k], dtype=np.float32) for k in self.variable_names()}
+        for msg in self._msg_MLPs.values():
+            msg.set_parameters(self._generic_params, scope=self.name + "/")
+        self._generic_device = {}
+
+    def _cell_params(self, v, device):
         import torch
+        key = (v, device)
+        if key not in self._generic_device:
+            base = "{}/{}_cell/layer_norm_basic_lstm_cell".format(self.name, v)
+            gates = ("input", "transform", "forget", "output", "state")
+            P = self._generic_params
+            to = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(device)
+            self._generic_device[key] = (to(P[base + "/kernel"]),
+                                         to(np.stack([P["{}/{}/gamma".format(base, g)] for g in gates])),
+                                         to(np.stack([P["{}/{}/beta".format(base, g)] for g in gates])))
+        return self._generic_device[key]
+
+    def _call_generic(self, adjacency_matrices, initial_embeddings, time_steps, LSTM_initial_states):
+        """graphnn.py:134-179 op by op: for every variable the update terms ( fun -> message MLP -> matrix
+        product | the matrix itself ) are concatenated and fed to its LayerNorm-LSTM cell; every variable reads
+        the time-t states.  CUDA tensors in, CUDA tensors out; ``fun`` entries are callables on CUDA tensors."""
+        import torch
+        from . import generic
+        if self.RNN_cell != "LayerNormBasicLSTMCell":
+            raise NotImplementedError("only LayerNormBasicLSTMCell cells are built (the reference's default, graphnn.py:14)")
+        if self._generic_params is None:
+            raise RuntimeError("Attempting to use uninitialized variables: call init_parameters() or set_parameters() first")
+        def dev_tensor(a):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+            return (t if t.is_cuda else t.cuda()).float().contiguous()
+        h = {v: dev_tensor(a) for v, a in initial_embeddings.items()}
+        device = next(iter(h.values())).device
+        c = {v: (dev_tensor(LSTM_initial_states[v]) if v in LSTM_initial_states else torch.zeros_like(h[v])) for v in h}
+        used = {u["mat"] for ups in self.loop.values() for u in ups if "mat" in u}
+        coo = {m: generic.CooMatrix(adjacency_matrices[m], device) for m in used
+               if any("var" in u and u.get("mat") == m for ups in self.loop.values() for u in ups)}
+        raw = {m: dev_tensor(adjacency_matrices[m]) for m in used
+               if any("var" not in u and u.get("mat") == m for ups in self.loop.values() for u in ups)}
+        for _ in range(int(time_steps)):
+            new_c, new_h = {}, {}
+            for v in self.var:
+                inputs = []
+                for u in self.loop[v]:
+                    if "var" in u:
+                        y = h[u["var"]]
+                        if "fun" in u:
+                            y = u["fun"](y)
+                        if "msg" in u:
+                            y = self._msg_MLPs[u["msg"]](y)
+                        if "mat" in u:
+                            y = coo[u["mat"]].matmul(y, transpose=bool(u.get("transpose?", False)))
+                        inputs.append(y)
+                    else:
+                        inputs.append(raw[u["mat"]])
+                x = inputs[0] if len(inputs) == 1 else torch.cat(inputs, dim=1)
+                kernel, gamma, beta = self._cell_params(v, device)
+                new_c[v], new_h[v] = generic.lnlstm(x, c[v], h[v], kernel, gamma, beta, activation=self.Cell_activation)
+            c, h = new_c, new_h
+        return {v: LSTMStateTuple(c=c[v], h=h[v]) for v in self.var}
+
+    def __call__(self, adjacency_matrices, initial_embeddings, time_steps, LSTM_initial_states={}):
+        """Runs ``time_steps`` message-passing iterations.
+
+        The TSP topology bound to an engine (build_network / Session) runs on the fused kernels:
+        adjacency_matrices[mat] is only shape-checked (the engine's plan holds the incidence structure);
+        initial_embeddings / LSTM_initial_states are row-major fp32 CUDA tensors [N_var, d].  Every other
+        case runs on the generic building blocks with this object's own parameters (init_parameters /
+        set_parameters).  Returns {var: LSTMStateTuple(c, h)} of CUDA tensors.
+        """
         self.check_run(adjacency_matrices, initial_embeddings, time_steps, LSTM_initial_states)
+        if self._engine is None or self._kernel_roles is None:
+            return self._call_generic(adjacency_matrices, initial_embeddings, time_steps, LSTM_initial_states)
+        import torch
         eng, R = self._engine, self._kernel_roles
         row, col = R["row_var"], R["col_var"]      # row variable = edges 'E', column variable = vertices 'V'
         zeros = lambda t: torch.zeros_like(t)

@@ -79,6 +79,11 @@ def build_network(d, mode="bf16x3", device=0):
             "E": [{"mat": "EV", "msg": "V_msg_E", "var": "V"}],                       # E(t+1) <- Eu(EV x V_msg_E(V(t)))
         },
         name="TSP")                                                          # model.py:57-94
+    if gnn._kernel_roles is None:
+        raise NotImplementedError(
+            "build_network(d=%r): the Session / engine path is built for the reference's default embedding size "
+            "d=64 (train.py:108); other sizes run only through GraphNN's generic CUDA path (GraphNN.__call__ "
+            "with its own parameters), not through the fused kernels behind sess.run" % (d,))
 
     E_vote_MLP = Mlp(layer_sizes=[d for _ in range(3)], activations=["relu" for _ in range(3)], output_size=1,
                      name="E_vote", name_internal_layers=True, kernel_initializer="xavier",
@@ -169,10 +174,18 @@ class Session(object):
         self._ensure_engine().set_optimizer_state(state)
 
     def load_weights(self, path):
+        """util.load_weights: tf.train.Saver().restore brings back every global variable, i.e. the Adam
+        slots and beta powers too (util.py:13-17), so a resumed run continues the same optimizer trajectory."""
+        ckpt = _params.load_checkpoint(path)
         self.set_variables(_params.load_weights(path))
+        opt = _params.named_to_optimizer_state(ckpt, self._gnn["_config"]["d"])
+        if opt is not None:
+            self.set_optimizer_state(opt)
 
     def save_weights(self, path):
-        _params.save_weights(self.get_variables(), path)
+        """util.save_weights: variables + Adam slots + beta powers (tf.train.Saver() default var_list)."""
+        opt = self.get_optimizer_state() if self._engine is not None else None
+        _params.save_weights(self.get_variables(), path, optimizer_state=opt)
 
     # -- run ------------------------------------------------------------------------
     def run(self, fetches, feed_dict=None):

@@ -89,15 +89,62 @@ def unflatten(blob, d=64):
     return {name: blob[off:off + n].reshape(shape).copy() for name, (off, n, shape) in table.items()}
 
 
-def save_weights(params, path):
-    """util.py:24-37 analogue: ``<path>/model.npz`` keyed by TF variable names."""
+# tf.train.Saver() without a var_list stores every GLOBAL variable (util.py:13,31): the trainable ones plus
+# AdamOptimizer's slots "<var>/Adam" (m), "<var>/Adam_1" (v) and the scalars beta1_power / beta2_power.
+ADAM_M, ADAM_V = "/Adam", "/Adam_1"
+
+
+def optimizer_state_to_named(state, d=64, beta1=0.9, beta2=0.999):
+    """{'m','v','step'} (flat blobs, Engine.get_optimizer_state) -> TF-named slot arrays."""
+    out = {}
+    for name, a in unflatten(state["m"], d).items():
+        out[name + ADAM_M] = a
+    for name, a in unflatten(state["v"], d).items():
+        out[name + ADAM_V] = a
+    out["beta1_power"] = np.float32(beta1 ** (int(state["step"]) + 1))     # TF keeps beta^(t+1) after t updates
+    out["beta2_power"] = np.float32(beta2 ** (int(state["step"]) + 1))
+    out["_adam_step"] = np.int64(state["step"])
+    return out
+
+
+def named_to_optimizer_state(named, d=64):
+    """Inverse of optimizer_state_to_named; None when the checkpoint holds no Adam slots."""
+    table, _ = param_offsets(d)
+    if not all((n + ADAM_M) in named and (n + ADAM_V) in named for n in table):
+        return None
+    m = flatten({n: named[n + ADAM_M] for n in table}, d)
+    v = flatten({n: named[n + ADAM_V] for n in table}, d)
+    if "_adam_step" in named:
+        step = int(named["_adam_step"])
+    elif "beta1_power" in named:                          # a converted TF checkpoint: beta1_power = 0.9^(t+1)
+        step = max(0, int(round(np.log(float(named["beta1_power"])) / np.log(0.9))) - 1)
+    else:
+        step = 0
+    return {"m": m, "v": v, "step": step}
+
+
+def save_weights(params, path, optimizer_state=None):
+    """util.py:24-37 analogue: ``<path>/model.npz`` keyed by TF variable names; with ``optimizer_state``
+    also the Adam slots and beta powers, like tf.train.Saver() (all global variables)."""
     os.makedirs(path, exist_ok=True)
-    np.savez(os.path.join(path, "model.npz"), **{k.replace("/", "|"): v for k, v in params.items()})
+    store = dict(params)
+    if optimizer_state is not None:
+        d = int(np.asarray(params["V_init"]).shape[-1])
+        store.update(optimizer_state_to_named(optimizer_state, d))
+    np.savez(os.path.join(path, "model.npz"), **{k.replace("/", "|"): v for k, v in store.items()})
 
 
-def load_weights(path):
-    """util.py:5-22 analogue; raises like the reference when the path is missing."""
+def load_checkpoint(path):
+    """Every array of the checkpoint, TF names -> numpy (variables, Adam slots, beta powers)."""
     if not os.path.exists(path):
         raise Exception("Path does not exist!")
     with np.load(os.path.join(path, "model.npz")) as z:
         return {k.replace("|", "/"): z[k] for k in z.files}
+
+
+def load_weights(path):
+    """util.py:5-22 analogue; raises like the reference when the path is missing.  Returns the trainable
+    variables only (see load_checkpoint / named_to_optimizer_state for the optimizer slots)."""
+    allv = load_checkpoint(path)
+    return {k: v for k, v in allv.items()
+            if not (k.endswith(ADAM_M) or k.endswith(ADAM_V) or k in ("beta1_power", "beta2_power", "_adam_step"))}
