@@ -21,6 +21,8 @@ for sizes, T in cases:
         t0 = time.time()
         eng = Engine(64, mode, 0)
         eng.set_params(params)
+        if os.environ.get("TSPGNN_FUSED"):
+            eng.set_option("fused", int(os.environ["TSPGNN_FUSED"]))
         eng.plan(nv, ne, EV.src, EV.dst)
         logits, preds = eng.forward_host(W, C, T)
         st = eng.get_states()

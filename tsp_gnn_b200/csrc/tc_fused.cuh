@@ -78,7 +78,14 @@ __device__ __forceinline__ void f_grid_sync(unsigned int* ctr, unsigned int targ
     unsigned int seen;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+#ifdef TSPGNN_DEBUG_WAIT
+      if (clock64() - t0 > 80000000LL) {
+        ptx::wait_timeout_record(0xFFFFF, target);
+        break;
+      }
+#else
       if (clock64() - t0 > 4000000000LL) __trap();      // a CTA that is not resident would hang the grid: fail loudly
+#endif
     } while (seen < target);
     __threadfence();
   }
@@ -89,6 +96,9 @@ __device__ __forceinline__ void f_grid_sync(unsigned int* ctr, unsigned int targ
 // per-CTA geometry of the persistent loop
 struct FGeo {
   int p0, rank, ntiles, nh, n_steps, nl_full, skip_last, nctas;
+  bool boot1;     // edge CTAs with >= 2 tiles: the x operand of the timestep's SECOND tile is built by warpgroup 1 at the
+                  // start of the timestep, in the h slot of the third tile (whose bulk copy waits until it is consumed)
+  __device__ __forceinline__ int boot1_slot(int base) const { return 1 + (base + 2) % nh; }
   __device__ __forceinline__ int nl(int t) const { return (skip_last && t == n_steps - 1) ? 0 : nl_full; }
   __device__ __forceinline__ int tile(int n) const { return 2 * (p0 + n) + rank; }
 };
@@ -125,12 +135,13 @@ struct FBars {
   uint64_t* acc_full;     // [2] an MMA group of warpgroup e completed (LSTM z, then every MLP layer)
   uint64_t* act_ready;    // [2] warpgroup e of BOTH CTAs: operand of the next MMA group written / accumulator drained
                           //     (only the even CTA's copy is used; the odd CTA's warps arrive on it remotely)
-  uint64_t* boot;         // x operand of the first tile written by the chain warps
+  uint64_t* boot;         // [2] x operand of the timestep's first tile (and, on edge CTAs, of its second tile, built
+                          //     in the third h slot while that is still free) written by the chain warps
   // twins in the EVEN CTA, arrived by the odd CTA's relay warp
   uint64_t* p_w;
   uint64_t* p_x_full;
   uint64_t* p_h_full;     // [3]
-  uint64_t* p_act_ready;  // [2] (unused)
+  uint64_t* p_boot1;      // twin of boot[1]
 };
 
 __device__ __forceinline__ FBars f_bars(uint8_t* base) {
@@ -142,11 +153,11 @@ __device__ __forceinline__ FBars f_bars(uint8_t* base) {
   r.h_full = b + 3;
   r.acc_full = b + 6;
   r.act_ready = b + 8;
-  r.boot = b + 10;
+  r.boot = b + 16;
   r.p_w = b + 11;
   r.p_x_full = b + 12;
   r.p_h_full = b + 13;
-  r.p_act_ready = b + 16;
+  r.p_boot1 = b + 10;
   return r;
 }
 
@@ -183,7 +194,7 @@ __device__ __forceinline__ void f_mma(const FArgs& a, uint8_t* smem, const FBars
     const int kb = 1 - half;      // the h k-block first: its bulk copy lands long before the gathered x operand is built
     ptx::tcgen05_fence_after();
     if (ptx::elect_one()) {
-      const int slot = (half == 0) ? 1 + hs : 0;
+      const int slot = (half == 0) ? 1 + hs : ((geo.boot1 && g == gbase + 1) ? geo.boot1_slot(gbase) : 0);
       const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};     // (A plane, B plane): cross terms first, then hi*hi
       const uint64_t aslot = slot_desc0 + static_cast<uint32_t>((slot * L::SLOT_BYTES) >> 4);
 #pragma unroll
@@ -208,7 +219,16 @@ __device__ __forceinline__ void f_mma(const FArgs& a, uint8_t* smem, const FBars
     const uint32_t par = (g / nh) & 1;
     return ptx::mbar_test(&b.h_full[hs], par) && ptx::mbar_test(&b.p_h_full[hs], par);
   };
-  auto x_ready = [&](int g) { return ptx::mbar_test(b.x_full, g & 1) && ptx::mbar_test(b.p_x_full, g & 1); };
+  // x operand of tile g.  x_full is consumed strictly one phase at a time (xf counts them over the launch);
+  // the second tile of a boot1 timestep is NOT on x_full: its operand is ready together with the first
+  // tile's, and two completions in a row would run a whole phase ahead of this (parity-testing) consumer.
+  uint32_t xf = 0;
+  int tstep = 0;
+  auto x_is_boot1 = [&](int g) { return geo.boot1 && g == gbase + 1; };
+  auto x_ready = [&](int g) {
+    if (x_is_boot1(g)) return ptx::mbar_test(&b.boot[1], tstep & 1) && ptx::mbar_test(b.p_boot1, tstep & 1);
+    return ptx::mbar_test(b.x_full, xf & 1) && ptx::mbar_test(b.p_x_full, xf & 1);
+  };
 
   ptx::mbar_wait(b.w, 0);
   ptx::mbar_wait(b.p_w, 0);
@@ -217,6 +237,7 @@ __device__ __forceinline__ void f_mma(const FArgs& a, uint8_t* smem, const FBars
     const int nl = (a.dbg & 4) ? 0 : geo.nl(t);
     const int base = t * ntiles, end = base + ntiles;
     gbase = base;
+    tstep = t;
     tl = (t == 0 && leader_lane) ? a.timeline : nullptr;
     // per stream: tile, next layer (nl = the LSTM item of tile + 2 comes next)
     int tile_[2], layer_[2] = {0, 0};
@@ -246,6 +267,7 @@ __device__ __forceinline__ void f_mma(const FArgs& a, uint8_t* smem, const FBars
             progress = true;
           }
         } else if (x_ready(lstm_g)) {
+          if (!x_is_boot1(lstm_g)) ++xf;
           issue_lstm_half(lstm_g, 1);
           lstm_h = false;
           ++lstm_g;
@@ -303,9 +325,19 @@ __device__ __forceinline__ void f_mma(const FArgs& a, uint8_t* smem, const FBars
         // scheduler with a warp of each chain warpgroup), alternating between the two streams
         nap ^= 1;
         const int e = (active[nap] && layer_[nap] < nl) ? nap : nap ^ 1;
-        if (active[e] && layer_[e] < nl) ptx::mbar_try_wait_ns(&b.act_ready[e], ar[e] & 1, 160);
-        else __nanosleep(100);
+        if (active[e] && layer_[e] < nl) ptx::mbar_try_wait_ns(&b.act_ready[e], ar[e] & 1, a.dbg >> 8 ? (a.dbg >> 8) : 160);
+        else __nanosleep(a.dbg >> 8 ? (a.dbg >> 8) : 100);
+#ifdef TSPGNN_DEBUG_WAIT
+        if (clock64() - spin0 > 40000000LL) {
+          // issuer stuck: record (pending LSTM tile - base, its h issued?, drained_ok - base, per stream tile - base / layer)
+          ptx::wait_timeout_record(0xE0000u | ((lstm_g - base) << 12) | (lstm_h ? 0x800 : 0) | ((drained_ok - base) << 6) |
+                                       ((tile_[0] - base) << 3) | (tile_[1] - base),
+                                   (layer_[0] << 4 | layer_[1]) & 1);
+          break;
+        }
+#else
         if (clock64() - spin0 > 4000000000LL) __trap();      // protocol bug: fail loudly instead of hanging
+#endif
       }
     }
     // the last tile of each stream: its drained arrival closes the stream's phase count for this timestep
@@ -327,11 +359,17 @@ __device__ __forceinline__ void f_forward(const FArgs& a, const FBars& b, const 
     __syncwarp();
   };
   forward(b.w, b.p_w, 0);
+  uint32_t xf = 0;      // x_full phases forwarded (see f_mma::x_ready)
   for (int t = 0; t < geo.n_steps; ++t) {
     for (int n = 0; n < geo.ntiles; ++n) {
       const int g = t * geo.ntiles + n, hs = g % geo.nh;
       forward(&b.h_full[hs], &b.p_h_full[hs], (g / geo.nh) & 1);
-      forward(b.x_full, b.p_x_full, g & 1);
+      if (geo.boot1 && n == 1) {
+        forward(&b.boot[1], b.p_boot1, t & 1);
+      } else {
+        forward(b.x_full, b.p_x_full, xf & 1);
+        ++xf;
+      }
     }
     if (t + 1 < geo.n_steps) f_grid_sync(a.grid_ctr, static_cast<unsigned int>(t + 1) * geo.nctas);
   }
@@ -363,32 +401,43 @@ __device__ __forceinline__ void f_producer(const FArgs& a, uint8_t* smem, const 
     const float* mV_in = a.mVb[t & 1];
     float* xV_in = a.xVb[t & 1];
     const int base = t * ntiles;
+    auto load_h = [&](int n) {
+      const int hs = (base + n) % geo.nh;
+      ptx::mbar_arrive_expect_tx(&b.h_full[hs], HP * PLANE_BYTES);
+      ptx::bulk_g2s(smem + L::SLOT_OFF + (1 + hs) * L::SLOT_BYTES,
+                    state + static_cast<int64_t>(geo.tile(n)) * tile_bytes(HP), HP * PLANE_BYTES, &b.h_full[hs]);
+    };
     if (gw == 0 && lane == 0) {
       // h planes of the first tiles of the timestep (every slot is free: the previous timestep is
-      // complete); later ones are fetched by the warpgroup that retires a slot
-      for (int n = 0; n < ntiles && n < geo.nh; ++n) {
-        const int hs = (base + n) % geo.nh;
-        ptx::mbar_arrive_expect_tx(&b.h_full[hs], HP * PLANE_BYTES);
-        ptx::bulk_g2s(smem + L::SLOT_OFF + (1 + hs) * L::SLOT_BYTES,
-                      state + static_cast<int64_t>(geo.tile(n)) * tile_bytes(HP), HP * PLANE_BYTES, &b.h_full[hs]);
-      }
+      // complete); later ones are fetched by the warpgroup that retires a slot.  With boot1 the third
+      // tile's slot first holds the x operand of the second tile: its copy is issued further down.
+      for (int n = 0; n < ntiles && n < geo.nh; ++n)
+        if (!(geo.boot1 && n == 2)) load_h(n);
     }
     __syncwarp();
+    const int first_gather = geo.boot1 ? 2 : 1;      // earlier tiles: x operand built by the chain warps
     int si[6], di[6];
 #pragma unroll
     for (int gi = 0; gi < 6; ++gi) si[gi] = di[gi] = 0;
-    if (ntiles > 1) load_idx(geo.tile(1), si, di);       // (tile 0: built by the chain warps)
+    if (ntiles > first_gather) load_idx(geo.tile(first_gather), si, di);
     for (int n = 0; n < ntiles; ++n) {
+      if (geo.boot1 && n == 1) continue;      // operand and its barrier (boot[1]) come from warpgroup 1
       const int tile = geo.tile(n), g = base + n;
       int sn[6], dn[6];
 #pragma unroll
       for (int gi = 0; gi < 6; ++gi) sn[gi] = dn[gi] = 0;
-      if (n >= 1 && n + 1 < ntiles) load_idx(tile + 2, sn, dn);   // next tile's column indices, a tile ahead
+      if (n >= first_gather && n + 1 < ntiles) load_idx(tile + 2, sn, dn);   // next tile's column indices, a tile ahead
       tl_mark(tl, 3, n, 0);
-      if (n >= 1) ptx::mbar_wait(b.x_empty, (g - 1) & 1);
+      if (n >= first_gather) {
+        // phase g - 1 of x_empty = LSTM(g - 1) has consumed its x operand.  Parity waits must be taken in
+        // order: the first gather of a boot1 timestep also passes the phase of the tile it skipped
+        if (geo.boot1 && n == 2) ptx::mbar_wait(b.x_empty, (g - 2) & 1);
+        ptx::mbar_wait(b.x_empty, (g - 1) & 1);
+      }
       tl_mark(tl, 3, n, 1);
-      if (n == 0) {
-        if (gw == 0) ptx::mbar_wait(b.boot, t & 1);
+      if (geo.boot1 && n == 2 && gw == 0 && lane == 0) load_h(2);      // LSTM(1) has consumed the x operand parked there
+      if (n < first_gather) {
+        ptx::mbar_wait(&b.boot[0], t & 1);      // (n == 0) every producer warp waits: each one arrives on x_full below
       } else {
         k1_fill_x<HP, IS_V, false>(xslot, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, mV_in, xV_in, si, di);
         ptx::fence_proxy_async_smem();
@@ -434,12 +483,22 @@ __device__ __forceinline__ void f_chain(const FArgs& a, uint8_t* smem, const FBa
     float* xV_out = a.xVb[(t + 1) & 1];
     const int base = t * ntiles;
     if (ntiles > 0) {
-      // x operand of the timestep's first tile: built by all eight chain warps, which have nothing
-      // else to do until the first accumulator is ready
-      k1_boot_fill_tile<HP, IS_V, false>(mV_in, xV_in, a.src, a.dst, smem + L::SLOT_OFF, warp - 4, lane, geo.tile(0));
+      // x operands of the timestep's first tile(s): built by the chain warps, which have nothing else to
+      // do until the first accumulator is ready -- warpgroup 0 the first tile and warpgroup 1 the second
+      // one (edge CTAs), or all eight warps the first tile
+      if (geo.boot1) {
+        if (e == 0)
+          k1_boot_fill_tile<HP, IS_V, false, 4>(mV_in, xV_in, a.src, a.dst, smem + L::SLOT_OFF, q4, lane, geo.tile(0));
+        else
+          k1_boot_fill_tile<HP, IS_V, false, 4>(mV_in, xV_in, a.src, a.dst,
+                                                smem + L::SLOT_OFF + geo.boot1_slot(base) * L::SLOT_BYTES, q4, lane,
+                                                geo.tile(1));
+      } else {
+        k1_boot_fill_tile<HP, IS_V, false, 8>(mV_in, xV_in, a.src, a.dst, smem + L::SLOT_OFF, warp - 4, lane, geo.tile(0));
+      }
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(b.boot);
+      if (lane == 0) ptx::mbar_arrive(&b.boot[geo.boot1 ? e : 0]);
     }
     for (int n = (e ^ base) & 1; n < ntiles; n += 2) {
       const int tile = geo.tile(n);
@@ -595,6 +654,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_step_kernel(const FArgs a) {
   geo.nl_full = is_v ? 4 : 3;
   geo.skip_last = a.skip_last_mlp;
   geo.nctas = static_cast<int>(gridDim.x);
+  geo.boot1 = !is_v && geo.ntiles > 1;
   const int tab_off = is_v ? L::TAB_OFF_V : L::TAB_OFF_E;
 
   if (tid == 0) {
@@ -603,7 +663,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_step_kernel(const FArgs a) {
     ptx::mbar_init(b.x_full, NUM_GATHER_WARPS);
     ptx::mbar_init(&b.act_ready[0], 8);      // four warps of the warpgroup in each CTA of the pair
     ptx::mbar_init(&b.act_ready[1], 8);
-    ptx::mbar_init(b.boot, 8);
+    ptx::mbar_init(&b.boot[0], geo.boot1 ? 4 : 8);
+    ptx::mbar_init(&b.boot[1], 4);
     ptx::fence_mbar_init();
     // weight images: parameters, not produced by the preceding kernel
     const int wm_bytes = (is_v ? 4 : 3) * L::WM_LAYER;

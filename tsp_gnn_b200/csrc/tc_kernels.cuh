@@ -183,25 +183,29 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
 // The x operand of a CTA's FIRST tile is built by the eight epilogue warps, which have nothing to do
 // until the first accumulator is ready and have the registers to keep every load in flight: the
 // first gather drops from three L2 round trips to one and the gather warps start on tile 1 at once.
-template <int HP, bool IS_V, bool NC = true>
+// NW = number of warps that share the tile (warp = 0 .. NW-1): 8 (two 8-row groups each) or 4 (four groups each).
+template <int HP, bool IS_V, bool NC = true, int NW = 8>
 __device__ __forceinline__ void k1_boot_fill_tile(const float* mV, float* xV,
                                                   const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                                   uint8_t* slot, int warp, int lane, int tile) {
+  constexpr int G = 16 / NW;
   struct { const float* mV; float* xV; const int32_t* src; const int32_t* dst; } a = {mV, xV, src, dst};
   const int r8 = lane & 7, cq = lane >> 3;
   const uint32_t slot_s = ptx::smem_u32(slot);
   const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
-  int s_[2] = {0, 0}, d_[2] = {0, 0};
+  int s_[G], d_[G];
+#pragma unroll
+  for (int gi = 0; gi < G; ++gi) s_[gi] = d_[gi] = 0;
   if (!IS_V) {
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
-      s_[gi] = __ldg(a.src + row0 + (2 * warp + gi) * 8 + r8);
-      d_[gi] = __ldg(a.dst + row0 + (2 * warp + gi) * 8 + r8);
+    for (int gi = 0; gi < G; ++gi) {
+      s_[gi] = __ldg(a.src + row0 + (G * warp + gi) * 8 + r8);
+      d_[gi] = __ldg(a.dst + row0 + (G * warp + gi) * 8 + r8);
     }
   }
 #pragma unroll
-  for (int gi = 0; gi < 2; ++gi) {
-    const int row = (2 * warp + gi) * 8 + r8;
+  for (int gi = 0; gi < G; ++gi) {
+    const int row = (G * warp + gi) * 8 + r8;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int chunk = cq + 4 * j;

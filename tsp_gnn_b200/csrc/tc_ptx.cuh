@@ -36,12 +36,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef TSPGNN_DEBUG_WAIT
+// Diagnosis build (-DTSPGNN_DEBUG_WAIT): a wait that times out records who waited on what and then
+// PROCEEDS, so that the kernel ends and the host can read the record (tspgnn_debug_wait_info).
+__device__ unsigned long long g_wait_info[16];
+__device__ __forceinline__ void wait_timeout_record(uint32_t bar_addr, uint32_t parity) {
+  const unsigned int slot = static_cast<unsigned int>(atomicAdd(&g_wait_info[0], 1ull));
+  if (slot < 15)
+    g_wait_info[1 + slot] = (static_cast<unsigned long long>(bar_addr & 0xFFFFFu) << 32) |
+                            (static_cast<unsigned long long>(parity & 1u) << 31) |
+                            (static_cast<unsigned long long>(blockIdx.x & 0xFFFu) << 12) | (threadIdx.x & 0xFFFu);
+}
+#endif
 // Bounded wait: a protocol bug traps (CUDA error on the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+#ifdef TSPGNN_DEBUG_WAIT
+    if (clock64() - t0 > 40000000LL) {
+      wait_timeout_record(smem_u32(bar), parity);
+      return;
+    }
+#else
     if (clock64() - t0 > 4000000000LL) __trap();
+#endif
   }
 }
 

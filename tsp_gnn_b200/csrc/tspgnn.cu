@@ -1200,6 +1200,15 @@ extern "C" int tspgnn_dense_ev_to_coo(const void* EV, int elem_size, int64_t row
   return 0;
 }
 
+#ifdef TSPGNN_DEBUG_WAIT
+// diagnosis build only: the record of the waits that timed out (count, then up to 15 entries)
+extern "C" int tspgnn_debug_wait_info(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out16, ptx::g_wait_info, 16 * sizeof(unsigned long long));
+  return e == cudaSuccess ? 0 : -2;
+}
+#endif
+
 // ------------------------------------------------------------------------------------
 // generic building blocks (stateless; device pointers on `device`)
 // ------------------------------------------------------------------------------------
