@@ -530,6 +530,7 @@ __device__ __forceinline__ void f_chain(const FArgs& a, uint8_t* smem, const FBa
         for (int l = 0; l < NL; ++l) {
           ptx::mbar_wait(&b.acc_full[e], af & 1);
           ++af;
+          if (e == 0 && l < 3) tl_mark(tl, 3, n, 3 + l);      // (trace: accumulator of layer l seen by warpgroup 0)
           ptx::tcgen05_fence_after();
           ptx::tmem_ld64(t_acc, v);
           const uint32_t bl = bias_s + l * 256;       // broadcast LDS.128: four bias values per load
