@@ -56,6 +56,12 @@ __global__ void __launch_bounds__(512, 1) tput_kernel(int iters, long long* out,
         y[k] = __ffma2_rn(y[k], y[(k + 1) & 7], y[(k + 2) & 7]);
         z[k].x = fmaxf(z[k].x, z[(k + 1) & 7].y);
         z[k].y = fminf(z[k].y, z[(k + 3) & 7].x);
+      } else if (KIND == 11) {  // two scalar FFMA, register operands
+        x[k].x = fmaf(x[k].x, x[(k + 1) & 7].x, x[(k + 2) & 7].x);
+        x[k].y = fmaf(x[k].y, x[(k + 1) & 7].y, x[(k + 2) & 7].y);
+      } else if (KIND == 12) {  // FMUL2 / FADD2 (two register pairs)
+        x[k] = __fmul2_rn(x[k], y[k]);
+        z[k] = __fadd2_rn(z[k], y[(k + 1) & 7]);
       } else if (KIND == 7) {   // scalar FFMA with constant operand c[][] immediate address
         x[k].x = fmaf(x[k].x, c_tab[k], c_tab[k + 8]);
         x[k].y = fmaf(x[k].y, c_tab[k + 16], c_tab[k + 24]);
@@ -96,6 +102,8 @@ int main() {
   run<5>("STS.128 + fence.proxy.async", d, sink, 8);
   run<6>("LDS.128 bcast + FFMA2", d, sink, 8);
   run<7>("FFMA x2 const-operand", d, sink, 16);
+  run<11>("FFMA x2 scalar regs", d, sink, 16);
+  run<12>("FMUL2 + FADD2", d, sink, 16);
   run<8>("slot: MUFU + 2 FFMA2", d, sink, 8);
   run<9>("slot: MUFU + 4 FMNMX", d, sink, 8);
   run<10>("slot: FFMA2 + 2 FMNMX", d, sink, 8);

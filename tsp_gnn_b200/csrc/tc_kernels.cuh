@@ -65,6 +65,7 @@ struct K1Args {
   const float* vdeg;     // [sumV_pad] number of incident edges of every vertex row
   const float* ln_tab;   // [2 cells][gamma'[5][64] | beta'[5][64]]: LayerNorm parameters as the epilogue wants them (see the prologue)
   long long* timeline;   // optional clock64() trace (tools/timeline.py), nullptr in production
+  int tl_slot;           // >= 0: also record %globaltimer at entry / prologue end / dependency wait / exit (launch-gap analysis)
 };
 
 struct K2Args {
@@ -88,6 +89,7 @@ struct K2Args {
   const float* bias_tab;   // [3 MLPs][4][64] biases (V_msg_E, E_msg_V, E_vote), coalesced copy for the prologue
   unsigned int* zero_word; // optional: cleared by this launch (grid barrier counter of the persistent kernel that follows)
   long long* timeline;
+  int tl_slot;
 };
 
 // (b4 of E_msg_V) . Kx of the V cell, centred per gate like the weight image (K1Args::vdeg)
@@ -98,6 +100,15 @@ constexpr int TL_ROLES = 4, TL_TILES = 64, TL_EVENTS = 8;
 __device__ __forceinline__ void tl_mark(long long* tl, int role, int tile, int ev) {
   if (tl != nullptr && tile < TL_TILES)
     tl[((static_cast<int64_t>(blockIdx.x) * TL_ROLES + role) * TL_TILES + tile) * TL_EVENTS + ev] = clock64();
+}
+
+// launch-gap trace: %globaltimer (ns, common to all SMs) of CTA-level events, slot [cta][role 3][tl_slot][ev]
+__device__ __forceinline__ void tl_gmark(long long* tl, int slot, int ev) {
+  if (tl != nullptr && slot >= 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    tl[((static_cast<int64_t>(blockIdx.x) * TL_ROLES + 3) * TL_TILES + slot) * TL_EVENTS + ev] = static_cast<long long>(t);
+  }
 }
 
 // contiguous, balanced range of tiles for CTA `i` of `n`
@@ -137,9 +148,63 @@ static_assert(K1Smem<2>::DYN_BYTES <= 232448, "K1 shared memory budget (227 KB)"
 // so every quarter-warp writes 128 contiguous bytes of shared memory (no bank conflicts).
 // NC = true: the messages are read through the non-coherent path (legal when a previous LAUNCH wrote them);
 // false: coherent loads, for the persistent kernel whose messages are written during the same launch.
-template <int HP, bool IS_V, bool NC = true>
-__device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64_t row0, const float* mV,
-                                          float* xV, const int (&si)[6], const int (&di)[6]) {
+// The gather is bound by L2 latency, not bandwidth (tools/microbench/datapipe.cu: ~800 cycles per round
+// trip, 14 B/clk per SM with 4 x 32-byte loads in flight per lane of three warps), so E rows are handled in
+// three batches of two 8-row groups: the 8 loads of a batch (64 registers) are all issued before the first
+// one is consumed.  k1_gather_load<B> issues batch B, k1_gather_store<B> adds, splits and stores it; the
+// caller issues batch 0 BEFORE it waits for the operand slot, so one of the three round trips of a tile
+// hides under that wait.
+template <bool NC>
+__device__ __forceinline__ void k1_gather_load(int b, int gw, int lane, const float* mV, const int (&si)[6],
+                                               const int (&di)[6], float (&u)[2][2][8], float (&w)[2][2][8]) {
+  const int cq = lane >> 3;
+#pragma unroll
+  for (int g2 = 0; g2 < 2; ++g2) {
+    const int gi = 2 * b + g2;
+    if (gw + NUM_GATHER_WARPS * gi < 16) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int chunk = cq + 4 * j;
+        if (NC) {
+          ptx::ldg256(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u[g2][j]);
+          ptx::ldg256(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w[g2][j]);
+        } else {
+          ptx::ldg256_coherent(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u[g2][j]);
+          ptx::ldg256_coherent(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w[g2][j]);
+        }
+      }
+    }
+  }
+}
+template <int HP>
+__device__ __forceinline__ void k1_gather_store(int b, uint8_t* slot, int gw, int lane, const float (&u)[2][2][8],
+                                                const float (&w)[2][2][8]) {
+  const int r8 = lane & 7, cq = lane >> 3;
+  const uint32_t slot_s = ptx::smem_u32(slot);
+#pragma unroll
+  for (int g2 = 0; g2 < 2; ++g2) {
+    const int g = gw + NUM_GATHER_WARPS * (2 * b + g2);
+    if (g < 16) {
+      const int row = g * 8 + r8;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int chunk = cq + 4 * j;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = u[g2][j][i] + w[g2][j][i];
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = slot_s + chunk * 2048 + row * 16;
+        ptx::sts128(off, hi);
+        if (HP == 2) ptx::sts128(off + PLANE_BYTES, lo);
+      }
+    }
+  }
+}
+
+// V rows: x = xV (then cleared).  Same lane -> (row, chunk) mapping; 5 % of the rows, kept simple.
+template <int HP>
+__device__ __forceinline__ void k1_fill_x_v(uint8_t* slot, int gw, int lane, int64_t row0, float* xV) {
   const int r8 = lane & 7, cq = lane >> 3;
   const uint32_t slot_s = ptx::smem_u32(slot);
 #pragma unroll
@@ -151,31 +216,34 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
       for (int j = 0; j < 2; ++j) {
         const int chunk = cq + 4 * j;
         float x[8];
-        if (IS_V) {
-          float4* p = reinterpret_cast<float4*>(xV + (row0 + row) * D + chunk * 8);
-          const float4 u0 = p[0], u1 = p[1];
-          p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-          p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
-          x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
-        } else {
-          float u[8], w[8];
-          if (NC) {
-            ptx::ldg256(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u);
-            ptx::ldg256(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w);
-          } else {
-            ptx::ldg256_coherent(mV + static_cast<int64_t>(si[gi]) * D + chunk * 8, u);
-            ptx::ldg256_coherent(mV + static_cast<int64_t>(di[gi]) * D + chunk * 8, w);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = u[i] + w[i];
-        }
+        float4* p = reinterpret_cast<float4*>(xV + (row0 + row) * D + chunk * 8);
+        const float4 u0 = p[0], u1 = p[1];
+        p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
+        x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
         uint4 hi, lo;
         split8(x, hi, lo);
         const uint32_t off = slot_s + chunk * 2048 + row * 16;
         ptx::sts128(off, hi);
         if (HP == 2) ptx::sts128(off + PLANE_BYTES, lo);
       }
+    }
+  }
+}
+
+// whole-tile form (all three batches back to back) for callers without a wait to hide a round trip under
+template <int HP, bool IS_V, bool NC = true>
+__device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64_t row0, const float* mV,
+                                          float* xV, const int (&si)[6], const int (&di)[6]) {
+  if (IS_V) {
+    k1_fill_x_v<HP>(slot, gw, lane, row0, xV);
+  } else {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      float u[2][2][8], w[2][2][8];
+      k1_gather_load<NC>(b, gw, lane, mV, si, di, u, w);
+      k1_gather_store<HP>(b, slot, gw, lane, u, w);
     }
   }
 }
@@ -189,7 +257,7 @@ __device__ __forceinline__ void k1_boot_fill_tile(const float* mV, float* xV,
                                                   const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                                   uint8_t* slot, int warp, int lane, int tile) {
   constexpr int G = 16 / NW;
-  struct { const float* mV; float* xV; const int32_t* src; const int32_t* dst; } a = {mV, xV, src, dst};
+  static_assert(G % 2 == 0, "groups are handled in pairs");
   const int r8 = lane & 7, cq = lane >> 3;
   const uint32_t slot_s = ptx::smem_u32(slot);
   const int64_t row0 = static_cast<int64_t>(tile) * TILE_ROWS;
@@ -199,41 +267,52 @@ __device__ __forceinline__ void k1_boot_fill_tile(const float* mV, float* xV,
   if (!IS_V) {
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      s_[gi] = __ldg(a.src + row0 + (G * warp + gi) * 8 + r8);
-      d_[gi] = __ldg(a.dst + row0 + (G * warp + gi) * 8 + r8);
+      s_[gi] = __ldg(src + row0 + (G * warp + gi) * 8 + r8);
+      d_[gi] = __ldg(dst + row0 + (G * warp + gi) * 8 + r8);
     }
   }
 #pragma unroll
-  for (int gi = 0; gi < G; ++gi) {
-    const int row = (G * warp + gi) * 8 + r8;
+  for (int gb = 0; gb < G; gb += 2) {       // two 8-row groups = 8 loads of 32 bytes in flight per lane
+    float u[2][2][8], w[2][2][8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int chunk = cq + 4 * j;
-      float x[8];
-      if (IS_V) {
-        float4* p = reinterpret_cast<float4*>(a.xV + (row0 + row) * D + chunk * 8);
-        const float4 u0 = p[0], u1 = p[1];
-        p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        x[0] = u0.x; x[1] = u0.y; x[2] = u0.z; x[3] = u0.w;
-        x[4] = u1.x; x[5] = u1.y; x[6] = u1.z; x[7] = u1.w;
-      } else {
-        float u[8], w[8];
-        if (NC) {
-          ptx::ldg256(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8, u);
-          ptx::ldg256(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8, w);
+    for (int g2 = 0; g2 < 2; ++g2) {
+      const int row = (G * warp + gb + g2) * 8 + r8;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int chunk = cq + 4 * j;
+        if (IS_V) {
+          float4* p = reinterpret_cast<float4*>(xV + (row0 + row) * D + chunk * 8);
+          const float4 u0 = p[0], u1 = p[1];
+          p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          p[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          u[g2][j][0] = u0.x; u[g2][j][1] = u0.y; u[g2][j][2] = u0.z; u[g2][j][3] = u0.w;
+          u[g2][j][4] = u1.x; u[g2][j][5] = u1.y; u[g2][j][6] = u1.z; u[g2][j][7] = u1.w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[g2][j][i] = 0.f;
+        } else if (NC) {
+          ptx::ldg256(mV + static_cast<int64_t>(s_[gb + g2]) * D + chunk * 8, u[g2][j]);
+          ptx::ldg256(mV + static_cast<int64_t>(d_[gb + g2]) * D + chunk * 8, w[g2][j]);
         } else {
-          ptx::ldg256_coherent(a.mV + static_cast<int64_t>(s_[gi]) * D + chunk * 8, u);
-          ptx::ldg256_coherent(a.mV + static_cast<int64_t>(d_[gi]) * D + chunk * 8, w);
+          ptx::ldg256_coherent(mV + static_cast<int64_t>(s_[gb + g2]) * D + chunk * 8, u[g2][j]);
+          ptx::ldg256_coherent(mV + static_cast<int64_t>(d_[gb + g2]) * D + chunk * 8, w[g2][j]);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = u[i] + w[i];
       }
-      uint4 hi, lo;
-      split8(x, hi, lo);
-      const uint32_t off = slot_s + chunk * 2048 + row * 16;
-      ptx::sts128(off, hi);
-      if (HP == 2) ptx::sts128(off + PLANE_BYTES, lo);
+    }
+#pragma unroll
+    for (int g2 = 0; g2 < 2; ++g2) {
+      const int row = (G * warp + gb + g2) * 8 + r8;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int chunk = cq + 4 * j;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = u[g2][j][i] + w[g2][j][i];
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const uint32_t off = slot_s + chunk * 2048 + row * 16;
+        ptx::sts128(off, hi);
+        if (HP == 2) ptx::sts128(off + PLANE_BYTES, lo);
+      }
     }
   }
 }
@@ -290,13 +369,24 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
       for (int gi = 0; gi < 6; ++gi) sn[gi] = dn[gi] = 0;
       if (n + 1 < ntiles) load_idx(tile + 1, sn, dn);     // next tile's column indices, a tile ahead
       tl_mark(tl, 3, n, 0);
+      float u[2][2][8], w[2][2][8];
+      if (!IS_V && n > 0) k1_gather_load<true>(0, gw, lane, a.mV, si, di, u, w);   // first round trip under the slot wait
       if (use >= 1) ptx::mbar_wait(&empty[slot], (use - 1) & 1);
       tl_mark(tl, 3, n, 1);
       if (n == 0) {
         if (gw == 0) ptx::mbar_wait(boot, 0);     // tile 0: operand written by the epilogue warps (k1_boot_fill)
       } else {
-        k1_fill_x<HP, IS_V>(ring + slot * L::SLOT_BYTES, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, a.mV, a.xV,
-                            si, di);
+        uint8_t* xs = ring + slot * L::SLOT_BYTES;
+        if (IS_V) {
+          k1_fill_x_v<HP>(xs, gw, lane, static_cast<int64_t>(tile) * TILE_ROWS, a.xV);
+        } else {
+          k1_gather_store<HP>(0, xs, gw, lane, u, w);
+#pragma unroll
+          for (int b = 1; b < 3; ++b) {
+            k1_gather_load<true>(b, gw, lane, a.mV, si, di, u, w);
+            k1_gather_store<HP>(b, xs, gw, lane, u, w);
+          }
+        }
         ptx::fence_proxy_async_smem();
       }
       __syncwarp();
@@ -400,6 +490,22 @@ __device__ __forceinline__ void row_stats64(uint32_t taddr, float& rstd, float& 
 __device__ __forceinline__ float row_rstd_centered64(uint32_t taddr) {
   float v[64];
   ptx::tmem_ld64(taddr, v);
+  float2 q2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = make_float2(v[2 * k], v[2 * k + 1]);
+    q2[k] = __fmul2_rn(t, t);
+  }
+#pragma unroll
+  for (int j = 4; j < 32; ++j) {
+    const float2 t = make_float2(v[2 * j], v[2 * j + 1]);
+    q2[j & 3] = __ffma2_rn(t, t, q2[j & 3]);
+  }
+  const float2 qt = __fadd2_rn(__fadd2_rn(q2[0], q2[1]), __fadd2_rn(q2[2], q2[3]));
+  return rsqrtf((qt.x + qt.y) * (1.0f / 64) + LN_EPS);
+}
+
+__device__ __forceinline__ float rstd_centered64_regs(const float (&v)[64]) {
   float2 q2[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -593,6 +699,178 @@ __device__ __forceinline__ void k1_cell_tile(uint8_t* gtile, int r, int lane, ui
   }
 }
 
+// Stand-alone cell kernel (K1), second form of the tile epilogue.  Differences from k1_cell_tile:
+//  * the statistics of the cell-state LayerNorm are accumulated in the gate pass (shifted one-pass sums
+//    around the row's first value instead of a separate two-pass read of the parked c~ row);
+//  * after the gate pass the o-gate row and the parked c~ row are copied into registers (128 values) and
+//    the accumulator goes back to the MMA warp at once: the MMAs of this warpgroup's next tile (3.2 k
+//    cycles of tensor pipe) run under the final pass instead of after it.  With two 256-column
+//    accumulators in TMEM that wait was 3 of every 12.5 k cycles of a warpgroup;
+//  * the gate LayerNorm statistics load the next gate's 64 columns while the current ones are squared.
+// The final pass is unrolled (its operands are register arrays).
+// (Measured and dropped: ONE reciprocal for all three logistic gates -- R = 1/(P.Q.E), c~ = num.R.E,
+// sigmoid(o) = R.P.Q, four transcendentals per column instead of five.  It shortens the epilogue by 1.5 k
+// cycles per tile but moves the o-gate work in front of the accumulator hand-back: the final pass (1.5 k)
+// no longer covers the next tile's MMAs (3.2 k) and the tile rate drops, K1 35.0 vs 31.2 us.  The pace of
+// this kernel is max((MMA + gate passes) / 2 accumulators, all passes / 2 warpgroups); both are ~5.2 k.)
+
+template <int HP, int CELL, bool CLAMP>
+__device__ __forceinline__ void k1_cell_tile2(uint8_t* gtile, int r, int lane, uint32_t t_acc, uint64_t* acc_full_bar,
+                                              uint32_t acc_parity, uint64_t* acc_empty_bar, uint32_t ln_s,
+                                              const float* __restrict__ vdeg_row, long long* tl, int e, int n) {
+  float4* cg = reinterpret_cast<float4*>(gtile + HP * PLANE_BYTES) + r;   // chunk q at cg[q * 128]
+  uint4* hg = reinterpret_cast<uint4*>(gtile) + r;                        // plane p, chunk ch at hg[p*1024 + ch*128]
+  // first 16 columns of the old cell state: issued before the accumulator is ready
+  float4 cur[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) cur[q] = cg[q * 128];
+  tl_mark(tl, e, n, 0);
+  ptx::mbar_wait(acc_full_bar, acc_parity);
+  tl_mark(tl, e, n, 1);
+  ptx::tcgen05_fence_after();
+
+  if (CELL == 0 && vdeg_row != nullptr) {
+    // folded E_msg_V output layer: z += deg(v) * (b4 . Kx)   (vertex tiles only, 5 % of the rows)
+    const float dg = *vdeg_row;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float zz[64];
+      ptx::tmem_ld64(t_acc + g * 64, zz);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) zz[i] = fmaf(dg, c_vfold_bias[g * 64 + i], zz[i]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float w16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w16[i] = zz[q * 16 + i];
+        ptx::tmem_st16(t_acc + g * 64 + q * 16, w16);
+      }
+    }
+  }
+
+  // ---- LayerNorm statistics of the four gates (centred by the weights: sum of squares only) ----
+  float rs0, rs1, rs2, rs3;
+  {
+    float va[64], vb[64];
+    ptx::tmem_ld64_nowait(t_acc, va);
+    ptx::tmem_ld64_nowait(t_acc + 64, vb);
+    ptx::tmem_wait_ld();
+    rs0 = rstd_centered64_regs(va);
+    ptx::tmem_ld64_nowait(t_acc + 128, va);
+    rs1 = rstd_centered64_regs(vb);
+    ptx::tmem_wait_ld();
+    ptx::tmem_ld64_nowait(t_acc + 192, vb);
+    rs2 = rstd_centered64_regs(va);
+    ptx::tmem_wait_ld();
+    rs3 = rstd_centered64_regs(vb);
+  }
+  tl_mark(tl, e, n, 2);
+  // ---- new cell state before its LayerNorm; parked in the (consumed) i-gate columns -------
+  float kshift = 0.f;
+  float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    float4 nx[4];
+    const int cn_ = (cc < 3) ? cc + 1 : cc;            // the 16 columns of c of the next iteration
+#pragma unroll
+    for (int q = 0; q < 4; ++q) nx[q] = cg[(cn_ * 4 + q) * 128];
+    float vi[16], vj[16], vf[16];
+    float4 gq[6];
+    ptx::tmem_ld16x3(t_acc + 0 * 64 + cc * 16, t_acc + 1 * 64 + cc * 16, t_acc + 2 * 64 + cc * 16, vi, vj, vf);
+    const uint32_t lcc = ln_s + cc * 64;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      if ((p & 1) == 0) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          gq[2 * g] = ptx::lds128f(lcc + g * 256 + (p >> 1) * 16);
+          gq[2 * g + 1] = ptx::lds128f(lcc + 1280 + g * 256 + (p >> 1) * 16);
+        }
+      }
+      const bool hiq = (p & 1) != 0;
+      const float2 gi = hiq ? make_float2(gq[0].z, gq[0].w) : make_float2(gq[0].x, gq[0].y);
+      const float2 bi = hiq ? make_float2(gq[1].z, gq[1].w) : make_float2(gq[1].x, gq[1].y);
+      const float2 gj = hiq ? make_float2(gq[2].z, gq[2].w) : make_float2(gq[2].x, gq[2].y);
+      const float2 bj = hiq ? make_float2(gq[3].z, gq[3].w) : make_float2(gq[3].x, gq[3].y);
+      const float2 gf = hiq ? make_float2(gq[4].z, gq[4].w) : make_float2(gq[4].x, gq[4].y);
+      const float2 bf = hiq ? make_float2(gq[5].z, gq[5].w) : make_float2(gq[5].x, gq[5].y);
+      const float2 in = __ffma2_rn(__fmul2_rn(make_float2(vi[2 * p], vi[2 * p + 1]), make_float2(rs0, rs0)), gi, bi);
+      const float2 jn = __ffma2_rn(__fmul2_rn(make_float2(vj[2 * p], vj[2 * p + 1]), make_float2(rs1, rs1)), gj, bj);
+      const float2 fn = __ffma2_rn(__fmul2_rn(make_float2(vf[2 * p], vf[2 * p + 1]), make_float2(rs2, rs2)), gf, bf);
+      const float4 c4 = cur[p >> 1];
+      const float2 cold = (p & 1) ? make_float2(c4.z, c4.w) : make_float2(c4.x, c4.y);
+      // c*sigmoid(f) + sigmoid(i)*relu(j) = (c*Q + relu(j)*P) / (P*Q), P = 1+e^-f, Q = 1+e^-i:
+      // one reciprocal for the two logistic functions
+      const float2 P = one_plus_ex2<CLAMP>(fn), Q = one_plus_ex2<CLAMP>(in);   // in / fn are already -x log2 e
+      const float2 den = __fmul2_rn(P, Q);
+      const float2 num = __ffma2_rn(cold, Q, __fmul2_rn(ptx::relu2(jn), P));
+      const float2 cn2 = __fmul2_rn(num, make_float2(ptx::rcp_approx(den.x), ptx::rcp_approx(den.y)));
+      vi[2 * p] = cn2.x;
+      vi[2 * p + 1] = cn2.y;
+      if (cc == 0 && p == 0) kshift = cn2.x;
+      const float2 t = __fadd2_rn(cn2, make_float2(-kshift, -kshift));
+      s1 = __fadd2_rn(s1, t);
+      s2 = __ffma2_rn(t, t, s2);
+    }
+    ptx::tmem_st16_nowait(t_acc + cc * 16, vi);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cur[q] = nx[q];
+  }
+  tl_mark(tl, e, n, 3);
+  // ---- o-gate row and c~ row into registers; the accumulator goes back to the MMA warp ----------
+  float vo[64], cs[64];
+  ptx::tmem_wait_st();
+  ptx::tmem_ld64_nowait(t_acc + 192, vo);
+  ptx::tmem_ld64_nowait(t_acc, cs);
+  ptx::tmem_wait_ld();
+  ptx::tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(acc_empty_bar);
+  // nn.moments of c~ from the shifted sums: mean = k + S1/64, var = S2/64 - (S1/64)^2
+  const float m1 = (s1.x + s1.y) * (1.0f / 64);
+  const float var = fmaxf(fmaf(-m1, m1, (s2.x + s2.y) * (1.0f / 64)), 0.f);
+  const float crs = rsqrtf(var + LN_EPS);
+  const float cm = -(kshift + m1) * crs;
+  tl_mark(tl, e, n, 4);
+  // ---- LayerNorm of the cell state, output gate, new h; straight to global memory -------------
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const uint32_t lcc = ln_s + cc * 64;
+    float2 c2[8];
+    uint32_t hi[8], lo[8];
+    float4 gq[4];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      if ((p & 1) == 0) {
+        gq[0] = ptx::lds128f(lcc + 3 * 256 + (p >> 1) * 16);
+        gq[1] = ptx::lds128f(lcc + 1280 + 3 * 256 + (p >> 1) * 16);
+        gq[2] = ptx::lds128f(lcc + 4 * 256 + (p >> 1) * 16);
+        gq[3] = ptx::lds128f(lcc + 1280 + 4 * 256 + (p >> 1) * 16);
+      }
+      const bool hiq = (p & 1) != 0;
+      const float2 go = hiq ? make_float2(gq[0].z, gq[0].w) : make_float2(gq[0].x, gq[0].y);
+      const float2 bo = hiq ? make_float2(gq[1].z, gq[1].w) : make_float2(gq[1].x, gq[1].y);
+      const float2 gs = hiq ? make_float2(gq[2].z, gq[2].w) : make_float2(gq[2].x, gq[2].y);
+      const float2 bs = hiq ? make_float2(gq[3].z, gq[3].w) : make_float2(gq[3].x, gq[3].y);
+      const int j = cc * 16 + 2 * p;
+      const float2 on = __ffma2_rn(__fmul2_rn(make_float2(vo[j], vo[j + 1]), make_float2(rs3, rs3)), go, bo);
+      c2[p] = __ffma2_rn(__ffma2_rn(make_float2(cs[j], cs[j + 1]), make_float2(crs, crs), make_float2(cm, cm)), gs, bs);
+      const float2 eo = one_plus_ex2<false>(on);   // on is already -x log2 e; 2^t = inf gives h = 0, the right limit
+      const float2 hn = __fmul2_rn(ptx::relu2(c2[p]), make_float2(ptx::rcp_approx(eo.x), ptx::rcp_approx(eo.y)));
+      ptx::split_bf16x2_p(hn, hi[p], lo[p]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      cg[(cc * 4 + q) * 128] = make_float4(c2[2 * q].x, c2[2 * q].y, c2[2 * q + 1].x, c2[2 * q + 1].y);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {   // two 16-B chunks of 8 bf16
+      hg[(cc * 2 + q) * 128] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      if (HP == 2) hg[1024 + (cc * 2 + q) * 128] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+  }
+  tl_mark(tl, e, n, 5);
+}
+
 template <int HP, int CELL, bool CLAMP>
 __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, uint32_t tmem, uint64_t* acc_full,
                                             uint64_t* acc_empty, int warp, int lane, long long* tl_, uint32_t ln_s,
@@ -605,8 +883,7 @@ __device__ __forceinline__ void k1_epilogue(uint8_t* state, int t0, int ntiles, 
   for (int n = e; n < ntiles; n += 2, ++use) {
     uint8_t* gtile = state + static_cast<int64_t>(t0 + n) * tile_bytes(HP);
     const float* vdeg_row = (vdeg != nullptr) ? vdeg + static_cast<int64_t>(t0 + n) * TILE_ROWS + r : nullptr;
-    k1_cell_tile<HP, CELL, CLAMP, false>(gtile, r, lane, t_acc, &acc_full[e], use & 1, &acc_empty[e], ln_s, vdeg_row, 0u,
-                                         tl, e, n);
+    k1_cell_tile2<HP, CELL, CLAMP>(gtile, r, lane, t_acc, &acc_full[e], use & 1, &acc_empty[e], ln_s, vdeg_row, tl, e, n);
   }
 }
 
@@ -626,6 +903,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(boot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  tl_gmark(a.timeline, a.tl_slot, 0);
   const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
   int t0, t1;
   if (is_v) tile_range(blockIdx.x - a.e_ctas, gridDim.x - a.e_ctas, a.tilesV, t0, t1);
@@ -669,11 +947,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
   const uint32_t ln_s = ptx::smem_u32(smem + L::LN_OFF);
   // everything above overlapped the tail of the previous kernel (programmatic dependent launch);
   // from here on the recurrent state and the messages it produced are read
+  tl_gmark(a.timeline, a.tl_slot, 1);
   ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
+  tl_gmark(a.timeline, a.tl_slot, 2);
 
   if (warp < 8) {
-    ptx::setmaxnreg_inc<200>();   // ... 256 x (200 - 168) = 8192 taken by the two epilogue warpgroups
+    ptx::setmaxnreg_inc<192>();   // ... 256 x (192 - 168) = 6144 taken by the two epilogue warpgroups
     if (ntiles > 0) {
       uint8_t* x0 = ring + (1 % L::NSLOT) * L::SLOT_BYTES;       // ring slot of sequence number 1 = x operand of tile 0
       if (is_v) k1_boot_fill<HP, true>(a, x0, warp, lane, t0);
@@ -691,7 +971,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
       else k1_epilogue<HP, 1, false>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s, a.vdeg);
     }
   } else {
-    ptx::setmaxnreg_dec<104>();   // 128 x (168 - 104) = 8192 registers back to the CTA pool ...
+    ptx::setmaxnreg_dec<120>();   // 128 x (168 - 120) = 6144 registers back to the CTA pool ...
     if (warp == 8) {
       if (ntiles > 0)
         k1_mma<HP>(wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles, a.timeline);
@@ -702,6 +982,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
+  tl_gmark(a.timeline, a.tl_slot, 3);
   if (warp == 8) ptx::tmem_dealloc(tmem, 512);
 }
 
@@ -937,6 +1218,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + K2_CHAINS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  tl_gmark(a.timeline, a.tl_slot, 0);
   const bool is_v = static_cast<int>(blockIdx.x) >= a.e_ctas;
   int t0, t1;
   if (is_v) tile_range(blockIdx.x - a.e_ctas, gridDim.x - a.e_ctas, a.tilesV, t0, t1);
@@ -972,8 +1254,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   ptx::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t bias_s = ptx::smem_u32(smem + L::BIAS_OFF);
+  tl_gmark(a.timeline, a.tl_slot, 1);
   ptx::grid_dependency_wait();       // prologue above overlaps the previous kernel's tail
   ptx::grid_launch_dependents();
+  tl_gmark(a.timeline, a.tl_slot, 2);
   if (a.zero_word != nullptr && blockIdx.x == 0 && tid == 0) *a.zero_word = 0u;
 
   if (warp < 4 * K2_CHAINS) {
@@ -998,6 +1282,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
+  tl_gmark(a.timeline, a.tl_slot, 3);
   if (warp == 12) ptx::tmem_dealloc(tmem, 256);
 }
 

@@ -702,7 +702,11 @@ static cudaError_t launch_pdl(void (*kernel)(const Args), int grid, int threads,
 static inline int grid_for(int64_t n, int per_block) { return static_cast<int>((n + per_block - 1) / per_block); }
 
 // CTAs are dedicated to edge tiles or to vertex tiles; `v_weight` is the measured cost of a vertex
-// tile relative to an edge tile (K1: the read-and-clear of xV makes its producer slower; K2: no scatter).
+// tile relative to an edge tile (K1: the read-and-clear of xV makes its producer slower and the degree-bias
+// pass its epilogue longer; K2: four layers, no scatter).  A CTA's tiles are whole: the split minimises the
+// makespan max(ceil(tilesE / e) , v_weight * ceil(tilesV / (grid - e))) -- a proportional split left the
+// few vertex CTAs with one tile too many (4 x 1.4 > 6 edge tiles) -- and, among equal makespans, the sum of
+// the two sides' spans (the lighter side's SMs go idle sooner and hand their power budget to the others).
 static void role_split(const tspgnn_ctx* h, int tilesE, int tilesV, double v_weight, int& grid, int& e_ctas) {
   const int total = tilesE + tilesV;
   grid = std::min(h->num_sms, total);
@@ -710,18 +714,30 @@ static void role_split(const tspgnn_ctx* h, int tilesE, int tilesV, double v_wei
     e_ctas = grid;
     return;
   }
-  e_ctas = static_cast<int>(std::lround(static_cast<double>(grid) * tilesE / (tilesE + v_weight * tilesV)));
-  e_ctas = std::max(1, std::min(e_ctas, grid - 1));
   if (grid < 2) {   // one SM-sized job: still needs both roles
     grid = 2;
     e_ctas = 1;
+    return;
+  }
+  double best = 1e300, best2 = 1e300;
+  e_ctas = 1;
+  for (int e = 1; e < grid; ++e) {
+    const double ce = static_cast<double>((tilesE + e - 1) / e);
+    const double cv = v_weight * static_cast<double>((tilesV + (grid - e) - 1) / (grid - e));
+    const double mk = std::max(ce, cv), sum = ce + cv;
+    if (mk < best - 1e-9 || (mk < best + 1e-9 && sum < best2 + 1e-9)) {   // ties: the larger edge share
+      best = mk;
+      best2 = sum;
+      e_ctas = e;
+    }
   }
 }
 
 template <int HP>
-static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, long long* timeline = nullptr) {
+static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, long long* timeline = nullptr, int tl_slot = -1) {
   K2Args a;
   a.timeline = timeline;
+  a.tl_slot = tl_slot;
   a.fold = (fold && !vote) ? 1 : 0;
   a.bias_tab = h->d_biastab;
   a.zero_word = h->d_gridctr;
@@ -747,9 +763,10 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, lon
 }
 
 template <int HP>
-static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, bool fold, long long* timeline = nullptr) {
+static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, bool fold, long long* timeline = nullptr, int tl_slot = -1) {
   K1Args a;
   a.timeline = timeline;
+  a.tl_slot = tl_slot;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = h->d_wlstm[1];
@@ -767,7 +784,7 @@ static int tc_launch_k1(tspgnn_ctx* h, cudaStream_t s, bool fold, long long* tim
   a.clampV = h->clamp_cell[0];
   a.clampE = h->clamp_cell[1];
   int grid;
-  role_split(h, a.tilesE, a.tilesV, fold ? 1.42 : 1.35, grid, a.e_ctas);
+  role_split(h, a.tilesE, a.tilesV, fold ? 1.55 : 1.4, grid, a.e_ctas);
   CUDA_TRY(launch_pdl(tc_lnlstm_kernel<HP>, grid, TC_THREADS, K1Smem<HP>::DYN_BYTES, s, a));
   LAUNCH_CHECK(h);
   return 0;
@@ -1150,6 +1167,13 @@ extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_
     // fused timestep kernel: messages, one traced launch, one launch without messages (buffers clean again)
     rc = step_messages(h, s, true);
     if (!rc) rc = (h->hp == 2) ? tc_launch_fused<2>(h, s, 2, true, d) : tc_launch_fused<1>(h, s, 2, true, d);
+  } else if (which == 3) {
+    // launch-gap trace: three timesteps of {K2, K1}, %globaltimer marks of every CTA in slots 56..61
+    rc = 0;
+    for (int i = 0; i < 3 && !rc; ++i) {
+      rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold, d, 56 + 2 * i) : tc_launch_k2<1>(h, s, false, h->fold, d, 56 + 2 * i);
+      if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold, d, 57 + 2 * i) : tc_launch_k1<1>(h, s, h->fold, d, 57 + 2 * i);
+    }
   } else if (which == 0) {
     rc = (h->hp == 2) ? tc_launch_k2<2>(h, s, false, h->fold) : tc_launch_k2<1>(h, s, false, h->fold);
     if (!rc) rc = (h->hp == 2) ? tc_launch_k1<2>(h, s, h->fold, d) : tc_launch_k1<1>(h, s, h->fold, d);
