@@ -62,6 +62,23 @@ __global__ void __launch_bounds__(512, 1) red_kernel(int mode, int nwarps, int i
           const float4 m = ptx::lds128f(tile_s + ((warp & 3) * 32 + rr) * row_stride + c16 * 16);
           ptx::red_add_v4(table + static_cast<int64_t>(vbase + di) * 64 + 4 * c16, m);
         }
+      } else if (mode == 5 || mode == 6) {
+        // mode 5: half-warps diverged, each issues its own 16-lane RED (one row per instruction)
+        // mode 6: 8 active lanes (half a row per instruction)
+        const int hw = lane >> 4, c16 = lane & 15;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int rr = 2 * i + hw;
+          const float4 m = ptx::lds128f(tile_s + ((warp & 3) * 32 + rr) * row_stride + c16 * 16);
+          if (mode == 5) {
+            if (hw == 0) ptx::red_add_v4(table + static_cast<int64_t>(base + rr) * 64 + 4 * c16, m);
+            __syncwarp();
+            if (hw == 1) ptx::red_add_v4(table + static_cast<int64_t>(base + rr) * 64 + 4 * c16, m);
+            __syncwarp();
+          } else {
+            if ((lane & 8) == 0) ptx::red_add_v4(table + static_cast<int64_t>(base + rr) * 64 + 4 * c16, m);
+          }
+        }
       } else if (mode == 2) {
         // thread = row: every lane reduces the 16 chunks of its own row (32 distinct rows per instruction)
         float* rowp = table + static_cast<int64_t>(base + lane) * 64;
@@ -97,7 +114,7 @@ int main() {
   cudaFuncSetAttribute(red_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   static long long h[148 * 16];
   for (int grid : {1, 148}) {
-    for (int mode : {0, 4}) {
+    for (int mode : {0, 5, 6}) {
       for (int nwarps : {1, 4, 12}) {
         for (int stride : {256, 272}) {
           if (stride == 256) continue;
@@ -110,7 +127,7 @@ int main() {
             for (int w = 0; w < nwarps; ++w) mx = h[b * 16 + w] > mx ? h[b * 16 + w] : mx;
           const double rows = (double)iters * 32 * nwarps;
           printf("grid=%3d %-5s warps=%2d stride=%d : %8.2f cycles per 256-B row per SM  (%6.1f B/clk/SM)  %s\n", grid,
-                 mode == 0 ? "RED4" : (mode == 2 ? "ROW" : (mode == 3 ? "PAIR" : (mode == 4 ? "REAL" : "BULK"))), nwarps, stride, mx / rows, rows * 256 / mx, cudaGetErrorString(e));
+                 mode == 0 ? "RED4" : (mode == 2 ? "ROW" : (mode == 3 ? "PAIR" : (mode == 4 ? "REAL" : (mode == 5 ? "HALF" : (mode == 6 ? "QUART" : "BULK"))))), nwarps, stride, mx / rows, rows * 256 / mx, cudaGetErrorString(e));
         }
       }
     }

@@ -25,6 +25,9 @@
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#ifndef TSPGNN_DBG_NO_RED
+#define TSPGNN_DBG_NO_RED 0
+#endif
 
 namespace tspgnn {
 
@@ -87,6 +90,9 @@ struct K2Args {
   // W4 (merged into its LSTM kernel) once per vertex instead of once per edge (K1Args::vdeg).
   int fold;
   const float* bias_tab;   // [3 MLPs][4][64] biases (V_msg_E, E_msg_V, E_vote), coalesced copy for the prologue
+  // scatter plan (tc_scatter_plan_kernel): per edge tile the 256 (row, endpoint vertex) pairs sorted by vertex
+  const uint8_t* ent_row;  // [tilesE][256] row of the tile
+  const int32_t* ent_v;    // [tilesE][256] vertex it adds to, -1 = padding
   unsigned int* zero_word; // optional: cleared by this launch (grid barrier counter of the persistent kernel that follows)
   long long* timeline;
   int tl_slot;
@@ -94,6 +100,7 @@ struct K2Args {
 
 // (b4 of E_msg_V) . Kx of the V cell, centred per gate like the weight image (K1Args::vdeg)
 __constant__ float c_vfold_bias[4 * D];
+
 
 // timeline slot: [cta][role 0..3][local tile 0..63][event 0..7]
 constexpr int TL_ROLES = 4, TL_TILES = 64, TL_EVENTS = 8;
@@ -1038,11 +1045,15 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
     const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
     const int slot = n % L::NSLOT;
     const uint32_t b_s = slots_s + slot * L::SLOT_BYTES;
-    // endpoints of this warp's 32 rows, fetched a whole layer chain ahead of the scatter that uses them
-    int my_s = -1, my_d = -1;
-    if ((ROLE == 1 || ROLE == 3) && row0 + q4 * 32 + lane < n_rows) {
-      my_s = __ldg(a.src + row0 + q4 * 32 + lane);
-      my_d = __ldg(a.dst + row0 + q4 * 32 + lane);
+    // this half-warp's 32 pairs of the tile's scatter plan (lane c16 holds pairs c16 and c16 + 16), fetched a
+    // whole layer chain ahead of the scatter that uses them
+    int e_row0 = 0, e_row1 = 0, e_v0 = -1, e_v1 = -1;
+    if (ROLE == 1 || ROLE == 3) {
+      const int64_t eo = static_cast<int64_t>(t0 + n) * (2 * TILE_ROWS) + (q4 * 2 + (lane >> 4)) * 32 + (lane & 15);
+      e_row0 = __ldg(a.ent_row + eo);
+      e_row1 = __ldg(a.ent_row + eo + 16);
+      e_v0 = __ldg(a.ent_v + eo);
+      e_v1 = __ldg(a.ent_v + eo + 16);
     }
     float v[64];
 #pragma unroll 1
@@ -1113,7 +1124,11 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
                        make_float4(v[4 * q] + bb.x, v[4 * q + 1] + bb.y, v[4 * q + 2] + bb.z, v[4 * q + 3] + bb.w));
         }
       }
-      __syncwarp();
+      // vertex rows: a warp reads back its own 32 rows; edge rows: the sorted pairs of a half-warp reference
+      // rows staged by any warp of the chain
+      if (ROLE == 0) __syncwarp();
+      else asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
+      tl_mark(tl, e, n, 5);
       const int64_t g0 = row0 + q4 * 32;
       const int hw = lane >> 4, c16 = lane & 15;
       if (ROLE == 0) {
@@ -1126,34 +1141,41 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
           }
         }
       } else {
-        // dst side: one vector reduction per row; src side accumulated over runs of equal src
-        // (rows of a complete graph are sorted by src, instance_loader.py:60)
-        int cur_s = -1;
+        // one reduction per GROUP of (row, endpoint) pairs with the same vertex (tc_scatter_plan_kernel):
+        // half-warp hwid walks pairs [32 hwid, 32 hwid + 32) of the tile's sorted list, two batches of 16
+        // row chunks in flight (shared-memory latency is several hundred cycles while the MMA operand
+        // fetch owns the read port), accumulates while the vertex stays the same and reduces when it changes.
+        int cur_v = -1;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + hw;
-          const int s = __shfl_sync(0xffffffffu, my_s, rr);
-          const int d = __shfl_sync(0xffffffffu, my_d, rr);
-          if (s >= 0) {
-            const float4 m = ptx::lds128f(b_s + stage_off(q4 * 32 + rr, c16));
-            ptx::red_add_v4(a.xV + static_cast<int64_t>(d) * D + 4 * c16, m);
-            if (s != cur_s) {
-              if (cur_s >= 0) ptx::red_add_v4(a.xV + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
-              cur_s = s;
-              acc = m;
-            } else {
-              acc.x += m.x; acc.y += m.y; acc.z += m.z; acc.w += m.w;
-            }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float4 m[16];
+          int vv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int rr = __shfl_sync(0xffffffffu, b ? e_row1 : e_row0, (lane & 16) | i);
+            vv[i] = __shfl_sync(0xffffffffu, b ? e_v1 : e_v0, (lane & 16) | i);
+            m[i] = ptx::lds128f(b_s + stage_off(rr, c16));
           }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool nw = vv[i] != cur_v;      // predicated, branch-free: the two half-warps change vertex at different pairs
+            ptx::red_add_v4_if(nw && cur_v >= 0 && !TSPGNN_DBG_NO_RED, a.xV + static_cast<int64_t>(cur_v < 0 ? 0 : cur_v) * D + 4 * c16, acc);
+            cur_v = vv[i];
+            acc.x = nw ? m[i].x : acc.x + m[i].x;
+            acc.y = nw ? m[i].y : acc.y + m[i].y;
+            acc.z = nw ? m[i].z : acc.z + m[i].z;
+            acc.w = nw ? m[i].w : acc.w + m[i].w;
+          }
+          if (b == 0) tl_mark(tl, e, n, 6);
         }
-        if (cur_s >= 0) ptx::red_add_v4(a.xV + static_cast<int64_t>(cur_s) * D + 4 * c16, acc);
+        if (cur_v >= 0) ptx::red_add_v4(a.xV + static_cast<int64_t>(cur_v) * D + 4 * c16, acc);
       }
     }
     // every warp of the chain is done with the slot: hand it back to the loader
     asm volatile("bar.sync %0, 128;" ::"r"(1 + e) : "memory");
     if (q4 == 0 && lane == 0) ptx::mbar_arrive(&slot_free[slot]);
-    tl_mark(tl, e, n, 5);
+    tl_mark(tl, e, n, 7);
   }
 }
 
@@ -1284,6 +1306,35 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_mlp_kernel(const K2Args a) {
   __syncthreads();
   tl_gmark(a.timeline, a.tl_slot, 3);
   if (warp == 12) ptx::tmem_dealloc(tmem, 256);
+}
+
+// Scatter plan of the message kernel: EV^T . msg adds every edge row to its two endpoint vertices
+// (instance_loader.py:63-66).  An SM retires about one 256-byte row reduction per 12.5 cycles
+// (tools/microbench/bulk_red.cu), so one reduction per (row, endpoint) costs 3.3 k cycles per tile.  Sorted
+// by vertex, the 256 (row, vertex) pairs of a tile form ~33 groups for a complete graph (every vertex of an
+// instance is touched ~8 times per tile): the message kernel sums a group in registers and issues ONE
+// reduction for it.  One CTA per tile, thread i = pair i (i < 128: src of row i, else dst of row i - 128);
+// rank by counting (256 keys).  Generic: any graph, any edge order.
+__global__ void __launch_bounds__(2 * TILE_ROWS) tc_scatter_plan_kernel(const int32_t* __restrict__ src,
+                                                                        const int32_t* __restrict__ dst, int64_t n_edges,
+                                                                        uint8_t* __restrict__ ent_row,
+                                                                        int32_t* __restrict__ ent_v) {
+  __shared__ int key[2 * TILE_ROWS];
+  const int i = threadIdx.x, row = i & (TILE_ROWS - 1);
+  const int64_t e = static_cast<int64_t>(blockIdx.x) * TILE_ROWS + row;
+  int v = 0x7fffffff;
+  if (e < n_edges) v = (i < TILE_ROWS) ? src[e] : dst[e];
+  key[i] = v;
+  __syncthreads();
+  int rank = 0;
+#pragma unroll 8
+  for (int j = 0; j < 2 * TILE_ROWS; ++j) {
+    const int kj = key[j];
+    rank += (kj < v || (kj == v && j < i)) ? 1 : 0;
+  }
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * (2 * TILE_ROWS) + rank;
+  ent_row[o] = static_cast<uint8_t>(row);
+  ent_v[o] = (v == 0x7fffffff) ? -1 : v;
 }
 
 // deg[v] = number of edge rows incident to vertex v (K1Args::vdeg); `deg` must be zeroed first

@@ -526,6 +526,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
+// predicated form: no branch around the reduction (run-length loops of the scatter stay convergent)
+__device__ __forceinline__ void red_add_v4_if(bool p, float* addr, float4 v) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(addr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(static_cast<int>(p))
+      : "memory");
+}
 __device__ __forceinline__ void red_add_v2(float* addr, float2 v) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
 }

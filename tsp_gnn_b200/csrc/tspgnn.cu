@@ -155,6 +155,8 @@ struct tspgnn_ctx {
   int64_t nE = 0, nV = 0, nE_pad = 0, nV_pad = 0;
   int tilesE = 0, tilesV = 0;
   int32_t *d_src = nullptr, *d_dst = nullptr, *d_vptr = nullptr, *d_vidx = nullptr;
+  uint8_t* d_ent_row = nullptr;               // [tilesE][256] scatter plan of the message kernel (tc_scatter_plan_kernel)
+  int32_t* d_ent_v = nullptr;
   int64_t* d_eoff = nullptr;
   // workspace
   float *Eh = nullptr, *Ec = nullptr, *Vh = nullptr, *Vc = nullptr;   // SIMT state / TC staging (Eh, Vh)
@@ -285,7 +287,7 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
     for (void* p : wp)
       if (p) cudaFree(p);
   }
-  void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2, h->d_gridctr};
+  void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2, h->d_gridctr, h->d_ent_row, h->d_ent_v};
   for (void* p : fp)
     if (p) cudaFree(p);
   void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg, h->d_lntab, h->d_biastab};
@@ -550,7 +552,9 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
     if (h->hp == 0) {
       if (dev_alloc(&h->Ec, nE_pad * D) || dev_alloc(&h->mE, nE_pad * D)) return TSPGNN_E_CUDA;
     } else {
-      if (dev_alloc(&h->stateE, nE_pad / TILE_ROWS * tile_bytes(h->hp))) return TSPGNN_E_CUDA;
+      if (dev_alloc(&h->stateE, nE_pad / TILE_ROWS * tile_bytes(h->hp)) || dev_alloc(&h->d_ent_row, 2 * nE_pad) ||
+          dev_alloc(&h->d_ent_v, 2 * nE_pad))
+        return TSPGNN_E_CUDA;
     }
     h->cap_E = nE_pad;
   }
@@ -648,6 +652,9 @@ extern "C" int tspgnn_plan(tspgnn_handle h, int n_instances, const int32_t* n_ve
     CUDA_TRY(cudaMemsetAsync(h->d_deg, 0, nV_pad * 4, nullptr));
     tc_degree_kernel<<<static_cast<int>((nE + 255) / 256), 256>>>(h->d_src, h->d_dst, nE, h->d_deg);
     CUDA_TRY(cudaGetLastError());
+    tc_scatter_plan_kernel<<<static_cast<int>(nE_pad / TILE_ROWS), 2 * TILE_ROWS>>>(h->d_src, h->d_dst, nE, h->d_ent_row,
+                                                                                    h->d_ent_v);
+    CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(cudaStreamSynchronize(nullptr));   // host vectors above go out of scope; the engine's stream is non-blocking
   h->B = n_instances;
@@ -740,6 +747,8 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, lon
   a.tl_slot = tl_slot;
   a.fold = (fold && !vote) ? 1 : 0;
   a.bias_tab = h->d_biastab;
+  a.ent_row = h->d_ent_row;
+  a.ent_v = h->d_ent_v;
   a.zero_word = h->d_gridctr;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
