@@ -346,6 +346,32 @@ def test_replanning_and_repeatability(mode):
     assert np.abs(outs[0] - outs[2]).max() <= 2e-6
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_shuffled_edge_rows_match_oracle(mode):
+    """The message kernel's scatter plan (per tile the (row, endpoint) pairs sorted by vertex) must not rely on
+    the reference's edge order (rows sorted by src, instance_loader.py:60): the rows of every instance are
+    shuffled, with a tail tile (sum E = 1157) and a sparse instance among them."""
+    EV, W, C, y, nv, ne = inst.synth_batch([30, 17, 25, 9, 21], seed=23, connectivity=0.85)
+    rs = np.random.RandomState(4)
+    src, dst, W, C = EV.src.copy(), EV.dst.copy(), W.copy(), C.copy()
+    off = 0
+    for m in ne:
+        p = off + rs.permutation(int(m))
+        src[off:off + m], dst[off:off + m] = src[p], dst[p]
+        W[off:off + m], C[off:off + m] = W[p], C[p]
+        off += int(m)
+    params = orc.init_params(64, seed=9, perturb_ln=True)
+    eng = make_engine(mode, params)
+    eng.plan(nv, ne, src, dst)
+    logits, preds = eng.forward_host(W, C, 5)
+    st = eng.get_states()
+    eng.close()
+    ref = orc.forward(params, src, dst, W, C, nv, ne, 5, dtype=np.float64)
+    assert np.abs(preds - ref["predictions"]).max() <= TOL_PRED[mode]
+    for k, v in (("E_h", st["E"][1]), ("E_c", st["E"][0]), ("V_h", st["V"][1]), ("V_c", st["V"][0])):
+        assert state_err(v.cpu().numpy(), ref[k]) <= TOL_STATE[mode], k
+
+
 @pytest.mark.parametrize("mode", ["simt", "bf16x3"])
 def test_cuda_path_matches_reference_graph_code_fixtures(mode):
     """Predictions of the CUDA path against the outputs of the reference's own model.py / graphnn.py /

@@ -259,7 +259,9 @@ __device__ __forceinline__ void k1_fill_x(uint8_t* slot, int gw, int lane, int64
 // until the first accumulator is ready and have the registers to keep every load in flight: the
 // first gather drops from three L2 round trips to one and the gather warps start on tile 1 at once.
 // NW = number of warps that share the tile (warp = 0 .. NW-1): 8 (two 8-row groups each) or 4 (four groups each).
-template <int HP, bool IS_V, bool NC = true, int NW = 8>
+// DEPWAIT: griddepcontrol.wait is executed after the column indices are loaded (they belong to the plan, not
+// to the preceding kernel's output) and before the first message is read.
+template <int HP, bool IS_V, bool NC = true, int NW = 8, bool DEPWAIT = false>
 __device__ __forceinline__ void k1_boot_fill_tile(const float* mV, float* xV,
                                                   const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                                                   uint8_t* slot, int warp, int lane, int tile) {
@@ -278,6 +280,7 @@ __device__ __forceinline__ void k1_boot_fill_tile(const float* mV, float* xV,
       d_[gi] = __ldg(dst + row0 + (G * warp + gi) * 8 + r8);
     }
   }
+  if (DEPWAIT) ptx::grid_dependency_wait();
 #pragma unroll
   for (int gb = 0; gb < G; gb += 2) {       // two 8-row groups = 8 loads of 32 bytes in flight per lane
     float u[2][2][8], w[2][2][8];
@@ -326,7 +329,7 @@ __device__ __forceinline__ void k1_boot_fill_tile(const float* mV, float* xV,
 
 template <int HP, bool IS_V>
 __device__ __forceinline__ void k1_boot_fill(const K1Args& a, uint8_t* slot, int warp, int lane, int tile) {
-  k1_boot_fill_tile<HP, IS_V>(a.mV, a.xV, a.src, a.dst, slot, warp, lane, tile);
+  k1_boot_fill_tile<HP, IS_V, true, 8, true>(a.mV, a.xV, a.src, a.dst, slot, warp, lane, tile);
 }
 
 template <int HP, bool IS_V>
@@ -367,6 +370,9 @@ __device__ __forceinline__ void k1_producer(const K1Args& a, uint8_t* state, uin
         }
       }
       __syncwarp();
+      // The recurrent state was written two launches ago (the message kernel in between only reads it):
+      // the first h operand is in flight before this launch waits for its predecessor's messages.
+      if (n == 0) ptx::grid_dependency_wait();
     }
     // ---- x operand (k-block 0) ---------------------------------------------------------
     {
@@ -952,23 +958,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
   ptx::tcgen05_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t ln_s = ptx::smem_u32(smem + L::LN_OFF);
-  // everything above overlapped the tail of the previous kernel (programmatic dependent launch);
-  // from here on the recurrent state and the messages it produced are read
+  // everything above overlapped the tail of the previous kernel (programmatic dependent launch).  Every
+  // role executes griddepcontrol.wait itself, as late as it can: only the messages (mV / xV) come from the
+  // preceding kernel, so column indices, the first h operand and the first cell-state chunk are requested
+  // before it.
   tl_gmark(a.timeline, a.tl_slot, 1);
-  ptx::grid_dependency_wait();
   ptx::grid_launch_dependents();
-  tl_gmark(a.timeline, a.tl_slot, 2);
 
   if (warp < 8) {
     ptx::setmaxnreg_inc<192>();   // ... 256 x (192 - 168) = 6144 taken by the two epilogue warpgroups
     if (ntiles > 0) {
       uint8_t* x0 = ring + (1 % L::NSLOT) * L::SLOT_BYTES;       // ring slot of sequence number 1 = x operand of tile 0
-      if (is_v) k1_boot_fill<HP, true>(a, x0, warp, lane, t0);
+      if (is_v) k1_boot_fill<HP, true>(a, x0, warp, lane, t0);   // (waits for the preceding kernel inside)
       else k1_boot_fill<HP, false>(a, x0, warp, lane, t0);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(boot);
+    } else {
+      ptx::grid_dependency_wait();
     }
+    tl_gmark(a.timeline, a.tl_slot, 2);
     const bool clamp = (is_v ? a.clampV : a.clampE) != 0;
     if (is_v) {
       if (clamp) k1_epilogue<HP, 0, true>(state, t0, ntiles, tmem, acc_full, acc_empty, warp, lane, a.timeline, ln_s, a.vdeg);
@@ -980,9 +989,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_lnlstm_kernel(const K1Args a
   } else {
     ptx::setmaxnreg_dec<120>();   // 128 x (168 - 120) = 6144 registers back to the CTA pool ...
     if (warp == 8) {
+      ptx::grid_dependency_wait();
       if (ntiles > 0)
         k1_mma<HP>(wsm, ring, bar_w, full, empty, acc_full, acc_empty, tmem, ntiles, a.timeline);
     } else {
+      if (ntiles == 0) ptx::grid_dependency_wait();
       if (is_v) k1_producer<HP, true>(a, state, ring, full, empty, boot, t0, ntiles, warp - 9, lane);
       else k1_producer<HP, false>(a, state, ring, full, empty, boot, t0, ntiles, warp - 9, lane);
     }
