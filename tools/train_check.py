@@ -25,6 +25,8 @@ ref = None if big else og.forward_backward(params, EV.src, EV.dst, W, C, nv, ne,
 print("oracle %.1fs, sumE %d sumV %d" % (time.time() - t0, int(np.sum(ne)), int(np.sum(nv))))
 eng = Engine(64, mode, 0)
 eng.set_params(params)
+if os.environ.get("TSPGNN_TRAIN_TC") is not None:
+    eng.set_option("train_tc", int(os.environ["TSPGNN_TRAIN_TC"]))
 eng.plan(nv, ne, EV.src, EV.dst)
 dev = torch.device("cuda", 0)
 s = eng.stream()

@@ -1,0 +1,499 @@
+// Tensor-core (tcgen05) row GEMM of the reverse pass (model.py:157-167 through tf.gradients):
+//   Y[rows, 64 NB] = epi( X[rows, 64 KB] . Wm (+ bias) ),   Wm = W or W^T of a parameter matrix
+// for row-major fp32 matrices addressed as (pointer, leading dimension) per 64-column block -- the same
+// contract as rowgemm_kernel (train_kernels.cuh), which stays the fp32 CUDA-core form of the `simt` mode.
+// Used for the recompute of the LSTM pre-activations z = [x, h] . K (KB 2, NB 4), for [dx, dh] = dz . K^T
+// (KB 4, NB 2) and for the 64-wide layers of the message / vote / initial-embedding MLPs, forward (recompute,
+// bias + ReLU) and reverse (W^T, ReLU mask or accumulation).
+//
+// Arithmetic: the bf16x3 scheme of the forward kernels (operands split into bf16 hi + lo, three MMAs per
+// product, fp32 accumulation in TMEM), so the reverse pass sees the same ~2^-16 relative operand error as
+// the forward pass whose state it differentiates.
+//
+// Structure (one persistent CTA per SM, 384 threads, tiles of 128 rows):
+//   warps 0-3, 4-7 : two epilogue warpgroups, one tile each.  The accumulator is read in the 16-lane
+//                    "quad" TMEM shape, so the four threads of a quad hold 32 contiguous bytes of a row and
+//                    the fp32 row-major output goes to global memory in full sectors without a shared-memory
+//                    transposition (8 rows x 32 bytes per warp instruction).
+//   warp  8        : tcgen05.mma issuer, owns the TMEM allocation (two accumulators of 64 NB columns)
+//   warps 9-11     : producers: 128 rows x 64 columns of X per k-block, fp32 -> bf16 hi / lo planes in the
+//                    un-swizzled K-major canonical layout (chunk-major, as the forward kernels' tile images),
+//                    through a ring of 32 KB slots
+// The B operand (both bf16 planes of Wm, up to 128 KB) is built once per CTA from the fp32 parameters.
+// The kernels are bound by the traffic of X and Y (128 x (KB + NB) x 256 bytes per tile), not by the MMAs.
+#pragma once
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_kernels.cuh"
+#include "train_kernels.cuh"
+
+namespace tspgnn {
+
+template <int KB, int NB>
+struct TRSmem {
+  static constexpr int N = 64 * NB;
+  static constexpr int W_BYTES = 2 * KB * N * 128;                 // [plane][kb]: image of N output features x 64 k
+  static constexpr int SLOT_BYTES = 2 * PLANE_BYTES;               // hi + lo planes of one k-block of a tile
+  static constexpr int NSLOT_MAX = (232448 - 1024 - W_BYTES) / SLOT_BYTES;
+  static constexpr int NSLOT = NSLOT_MAX > 4 ? 4 : NSLOT_MAX;
+  static constexpr int RING_OFF = W_BYTES;
+  static constexpr int BAR_OFF = RING_OFF + NSLOT * SLOT_BYTES;
+  static constexpr int NBAR = 2 * NSLOT + 4;
+  static constexpr int TOTAL = BAR_OFF + 8 * NBAR + 16;
+  static constexpr int DYN_BYTES = TOTAL + 128;
+  static_assert(NSLOT >= 2, "row GEMM: operand ring needs two slots");
+  static_assert(DYN_BYTES <= 232448, "row GEMM: shared memory budget (227 KB)");
+};
+
+template <int KB, int NB, bool TRANS, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemmArgs a) {
+  using L = TRSmem<KB, NB>;
+  constexpr int N = 64 * NB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* wsm = smem;
+  uint8_t* ring = smem + L::RING_OFF;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty = full + L::NSLOT;
+  uint64_t* acc_full = empty + L::NSLOT;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles_all = static_cast<int>((a.n_rows + TILE_ROWS - 1) / TILE_ROWS);
+  int t0, t1;
+  tile_range(blockIdx.x, gridDim.x, n_tiles_all, t0, t1);
+  const int ntiles = t1 - t0;
+
+  if (tid == 0) {
+    for (int s = 0; s < L::NSLOT; ++s) {
+      ptx::mbar_init(&full[s], NUM_GATHER_WARPS);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&acc_empty[s], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
+  // ---- B operand: Wm[k, n] (TRANS: Ws[n, k], else Ws[k, n]; zero outside w_rows x w_cols), bf16 hi / lo images.
+  // One 16-byte chunk = 8 consecutive k of one output feature n; consecutive threads take consecutive n.
+  for (int i = tid; i < KB * 8 * N; i += TC_THREADS) {
+    const int n = i % N, kc = i / N;              // kc: chunk of 8 k-values, 0 .. 8 KB - 1
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kc * 8 + j;
+      float x = 0.f;
+      if (!TRANS) {
+        if (k < a.w_rows && n < a.w_cols) x = __ldg(a.w + static_cast<int64_t>(k) * a.ldw + n);
+      } else {
+        if (n < a.w_rows && k < a.w_cols) x = __ldg(a.w + static_cast<int64_t>(n) * a.ldw + k);
+      }
+      v[j] = x;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    const int kb = kc >> 3, kin = kc & 7;
+    uint8_t* p = wsm + static_cast<size_t>(kb) * (N * 128) + kin * (N * 16) + n * 16;
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + static_cast<size_t>(KB) * (N * 128)) = lo;
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    // ---- epilogue: accumulator -> (+bias, ReLU / mask / accumulate) -> row-major fp32 Y -----------------
+    const int e = warp >> 2, q4 = warp & 3;
+    const int tq0 = lane & 3, tq1 = lane >> 2;
+    const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 256;
+    int use = 0;
+    for (int n = e; n < ntiles; n += 2, ++use) {
+      const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS + q4 * 32 + tq1;   // + 8 m
+      // ReLU mask / previous output of a 64-wide layer: requested before the accumulator is waited for
+      // (otherwise every tile pays a second memory round trip between the TMEM read and the store)
+      constexpr bool PRE = (NB == 1) && ((EPI & (EPI_MASK | EPI_ACCUM)) != 0);
+      float2 pre[PRE ? 4 : 1][PRE ? 8 : 1];
+      if (PRE) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int64_t row = row0 + 8 * m;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            pre[m][k] = make_float2((EPI & EPI_MASK) ? 1.f : 0.f, (EPI & EPI_MASK) ? 1.f : 0.f);
+            if (row < a.n_rows) {
+              const float* src = (EPI & EPI_MASK) ? a.mask + row * a.mld : a.y[0] + row * a.yld[0];
+              pre[m][k] = *reinterpret_cast<const float2*>(src + 2 * tq0 + 8 * k);
+            }
+          }
+        }
+      }
+      ptx::mbar_wait(&acc_full[e], use & 1);
+      ptx::tcgen05_fence_after();
+#pragma unroll 1
+      for (int nb = 0; nb < NB; ++nb) {
+        float qa[32], qb[32];     // rows tq1, tq1 + 8 (qa) and tq1 + 16, tq1 + 24 (qb); reg[4k + 2hi + j] = column 8k + 2 tq0 + j
+        ptx::tmem_ld_quad64(t_acc + nb * 64, qa, qb);
+        if (nb == NB - 1) {       // last TMEM read of this tile: hand the accumulator back
+          ptx::tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[e]);
+        }
+        float* yp = a.y[nb];
+        const int yld = a.yld[nb];
+        float2 bq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int col = nb * 64 + 8 * k + 2 * tq0;
+          bq[k].x = (a.bias != nullptr && col < a.bias_n) ? __ldg(a.bias + col) : 0.f;
+          bq[k].y = (a.bias != nullptr && col + 1 < a.bias_n) ? __ldg(a.bias + col + 1) : 0.f;
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int64_t row = row0 + 8 * m;
+          if (row < a.n_rows) {
+            float* yr = yp + row * yld + 2 * tq0;
+            const float* mr = (EPI & EPI_MASK) ? a.mask + row * a.mld + 2 * tq0 : nullptr;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int ix = 4 * k + 2 * (m & 1);
+              float2 v = make_float2(((m < 2) ? qa : qb)[ix] + bq[k].x, ((m < 2) ? qa : qb)[ix + 1] + bq[k].y);
+              if (EPI & EPI_RELU) v = ptx::relu2(v);
+              if (EPI & EPI_MASK) {
+                const float2 mk = PRE ? pre[m][k] : *reinterpret_cast<const float2*>(mr + 8 * k);
+                v.x = (mk.x > 0.f) ? v.x : 0.f;
+                v.y = (mk.y > 0.f) ? v.y : 0.f;
+              }
+              if (EPI & EPI_ACCUM) {
+                const float2 o = (PRE && !(EPI & EPI_MASK)) ? pre[m][k] : *reinterpret_cast<const float2*>(yr + 8 * k);
+                v.x += o.x;
+                v.y += o.y;
+              }
+              *reinterpret_cast<float2*>(yr + 8 * k) = v;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------
+    constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, N);
+    const uint64_t adesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(ring), 2048, 128);
+    const uint64_t bdesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(wsm), N * 16, 128);
+    for (int n = 0; n < ntiles; ++n) {
+      const int acc = n & 1, k_use = n >> 1;
+      if (k_use >= 1) ptx::mbar_wait(&acc_empty[acc], (k_use - 1) & 1);
+      const uint32_t d_tmem = tmem + acc * 256;
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        const int seq = n * KB + kb, slot = seq % L::NSLOT, suse = seq / L::NSLOT;
+        ptx::mbar_wait(&full[slot], suse & 1);
+        ptx::tcgen05_fence_after();
+        if (ptx::elect_one()) {
+          const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};        // (A plane, B plane): lo.hi, hi.lo, hi.hi
+          const uint64_t aslot = adesc0 + static_cast<uint32_t>((slot * L::SLOT_BYTES) >> 4);
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16_ss(d_tmem, aslot + ((pa_[cb] * PLANE_BYTES + k * 4096) >> 4),
+                                bdesc0 + static_cast<uint32_t>(((pb_[cb] * KB + kb) * (N * 128) + k * (2 * N * 16)) >> 4), IDESC,
+                                (kb | cb | k) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[slot]);
+          if (kb == KB - 1) ptx::umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---- producers: X block -> bf16 hi / lo operand planes ------------------------------------------------
+    const int gw = warp - 9;
+    const int r8 = lane & 7, cq = lane >> 3;
+    for (int n = 0; n < ntiles; ++n) {
+      const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        const int seq = n * KB + kb, slot = seq % L::NSLOT, suse = seq / L::NSLOT;
+        const float* xp = a.x[kb];
+        const int xld = a.xld[kb];
+        const uint32_t slot_s = ptx::smem_u32(ring + slot * L::SLOT_BYTES);
+        if (suse >= 1) ptx::mbar_wait(&empty[slot], (suse - 1) & 1);
+#pragma unroll
+        for (int gb = 0; gb < 6; gb += 2) {             // two 8-row groups = eight 16-byte loads in flight per lane
+          float4 u[2][2][2];
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const int g = gw + NUM_GATHER_WARPS * (gb + g2);
+            const int64_t row = row0 + g * 8 + r8;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              u[g2][j][0] = u[g2][j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (g < 16 && row < a.n_rows) {
+                const float4* p = reinterpret_cast<const float4*>(xp + row * xld + (cq + 4 * j) * 8);
+                u[g2][j][0] = p[0];
+                u[g2][j][1] = p[1];
+              }
+            }
+          }
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const int g = gw + NUM_GATHER_WARPS * (gb + g2);
+            if (g < 16) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const float x[8] = {u[g2][j][0].x, u[g2][j][0].y, u[g2][j][0].z, u[g2][j][0].w,
+                                    u[g2][j][1].x, u[g2][j][1].y, u[g2][j][1].z, u[g2][j][1].w};
+                uint4 hi, lo;
+                split8(x, hi, lo);
+                const uint32_t off = slot_s + (cq + 4 * j) * 2048 + (g * 8 + r8) * 16;
+                ptx::sts128(off, hi);
+                ptx::sts128(off + PLANE_BYTES, lo);
+              }
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&full[slot]);
+      }
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc(tmem, 512);
+}
+
+
+// =====================================================================================================
+// dW[kb*64 + k, nb*64 + n] += sum_r X[r, kb*64 + k] * dY[r, nb*64 + n],   db[n] += sum_r dY[r, n]
+// on tcgen05 (the contract of xtdy_kernel: every kernel / bias gradient of the reverse pass).
+//
+// The contraction runs over ROWS.  The chunk-major tile image the forward kernels use as a K-major A operand
+// (element (row, col) at (col / 8) * 2048 + row * 16 + (col % 8) * 2) is at the same time the canonical
+// un-swizzled MN-major layout of the matrix [col][row]: 8 consecutive rows (k) of 8 columns (mn) form the
+// 128-byte core matrix, core matrices are 128 bytes apart along k (LBO) and 2048 bytes apart along mn (SBO).
+// So one image of the X tile is the A operand (M = features of X, K = rows) and one image of the dY tile the
+// B operand (N = 64 columns of dY, K = rows) of  D[M, N] += A . B^T  with both major bits set in the
+// instruction descriptor; a 128-row tile is 8 MMAs of K = 16 per operand-plane combination, bf16x3 as everywhere.
+// D accumulates in TMEM over all tiles of the CTA (128 lanes x 64 columns).
+//
+// Grid (gx, 64-column blocks of dY): CTA (bx, nb) owns a contiguous range of row tiles.  288 threads:
+//   warps 0-7 : producers (X and dY tiles: fp32 -> bf16 hi / lo images, two stages of 96 KB); afterwards
+//               warps 0-3 read the accumulator (lane = feature) and write the CTA's partial to scratch
+//   warp  8   : tcgen05.mma issuer
+// The bias gradient is the row of D that belongs to an extra all-ones feature of X (feature 64; only when
+// X has 64 features: every biased layer of the model does).  CTA bx adds its partial to slot bx of a blob of
+// per-CTA partial gradients laid out like the parameters ([slots][total]; launches of one stream are ordered and
+// the two streams of the reverse pass touch different tensors, so plain read-modify-write is enough);
+// grad_partial_reduce_kernel sums the slots in fixed order once at the end of the reverse pass: deterministic, no
+// floating-point atomics, and no per-launch reduction (a last-CTA reduction of 32 partials cost 30 us per launch).
+// =====================================================================================================
+constexpr int XT2_THREADS = 288;
+constexpr int XT2_STAGE = 2 * 2 * PLANE_BYTES + 2 * PLANE_BYTES;   // X hi/lo (128 features) + dY hi/lo (64 columns) = 96 KB
+
+struct Xtdy2Args {
+  XtdyArgs x;            // the contract of xtdy_kernel (dw / db are only used for their offsets, see below)
+  int kblocks;           // 64-column blocks of X (1 or 2)
+  float* pblob;          // [slots][total] per-CTA partial gradients, slot = blockIdx.x
+  int64_t total;         // floats per slot (= size of the parameter blob)
+  int64_t dw_off, db_off;  // offsets of dW / db inside a slot (db_off < 0: no bias)
+};
+
+struct XT2Smem {
+  static constexpr int BAR_OFF = 2 * XT2_STAGE;
+  static constexpr int TOTAL = BAR_OFF + 8 * 5 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 128;
+};
+static_assert(XT2Smem::DYN_BYTES <= 232448, "xtdy: shared memory budget (227 KB)");
+
+// kind::f16 instruction descriptor, bf16 A / B, fp32 D, BOTH operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) {
+  return ptx::umma_idesc_bf16(m, n) | (1u << 15) | (1u << 16);
+}
+
+__global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args q) {
+  const XtdyArgs& a = q.x;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + XT2Smem::BAR_OFF);   // [2]
+  uint64_t* empty = full + 2;                                              // [2]
+  uint64_t* acc_full = empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = blockIdx.y;
+  const int KB = q.kblocks;
+  const bool ones = (a.db != nullptr) && KB == 1;      // bias gradient through the all-ones feature 64
+  const int n_tiles_all = static_cast<int>((a.n_rows + TILE_ROWS - 1) / TILE_ROWS);
+  int t0, t1;
+  tile_range(blockIdx.x, gridDim.x, n_tiles_all, t0, t1);
+  const int ntiles = t1 - t0;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&full[s], 8);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(acc_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(tmem_slot, 64);
+  // feature chunks the producers never write (X has 64 or 128 features, M is always 128) must read as zero
+  for (int i = tid; i < 2 * XT2_STAGE / 16; i += XT2_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  ptx::fence_proxy_async_smem();
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    // ---- producers ------------------------------------------------------------------------------------
+    // a warp task = 8 rows x 4 chunks of 8 columns (lane -> row lane & 7, chunk lane >> 3): every lane reads 32
+    // contiguous bytes, every quarter-warp writes 128 contiguous bytes of an operand plane
+    const int r8 = lane & 7, cq = lane >> 3;
+    const int quads = 2 * KB + 2;                       // chunk quads per row group: X (2 per 64 columns), dY (2)
+    const int ntask = 16 * quads;
+    const float* dyp = a.dy + nb * 64;
+    for (int n = 0; n < ntiles; ++n) {
+      const int st = n & 1, use = n >> 1;
+      const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
+      uint8_t* stage = smem + st * XT2_STAGE;
+      const uint32_t xs = ptx::smem_u32(stage), ys = xs + 4 * PLANE_BYTES;
+      if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
+#pragma unroll 1
+      for (int tb = warp; tb < ntask; tb += 64) {       // eight tasks (sixteen 16-byte loads) in flight per lane
+        float4 u[8][2];
+        uint32_t dst[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int task = tb + 8 * i;
+          u[i][0] = u[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[i] = 0u;
+          if (task < ntask) {
+            const int g = task / quads, qd = task % quads;
+            const int64_t row = row0 + g * 8 + r8;
+            const float* p;
+            if (qd < 2 * KB) {
+              const int kb = qd >> 1, chunk = (qd & 1) * 4 + cq;           // chunk inside the 64-column block
+              p = (kb == 0 ? a.x[0] : a.x[1]) + row * (kb == 0 ? a.xld[0] : a.xld[1]) + chunk * 8;
+              dst[i] = xs + (kb * 8 + chunk) * 2048 + (g * 8 + r8) * 16;
+            } else {
+              const int chunk = (qd - 2 * KB) * 4 + cq;
+              p = dyp + row * a.dyld + chunk * 8;
+              dst[i] = ys + chunk * 2048 + (g * 8 + r8) * 16;
+            }
+            if (row < a.n_rows) {
+              u[i][0] = reinterpret_cast<const float4*>(p)[0];
+              u[i][1] = reinterpret_cast<const float4*>(p)[1];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (tb + 8 * i < ntask) {
+            const float x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const bool is_x = dst[i] < ys;
+            ptx::sts128(dst[i], hi);
+            ptx::sts128(dst[i] + (is_x ? 2 * PLANE_BYTES : PLANE_BYTES), lo);
+          }
+        }
+      }
+      if (ones && warp < 4) {
+        // feature 64 (chunk 8, element 0) = 1 for the valid rows of the tile: its row of D is colsum(dY)
+        const int r = warp * 32 + lane;
+        const uint32_t one = (row0 + r < a.n_rows) ? 0x3F80u : 0u;       // bf16(1.0) in the low half
+        ptx::sts128(xs + 8 * 2048 + r * 16, make_uint4(one, 0u, 0u, 0u));
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full[st]);
+    }
+    // ---- partial of this CTA: lane = feature, 64 columns, added to this CTA's slot ------------------------------
+    if (warp < 4 && ntiles > 0) {
+      float v[64];
+      ptx::mbar_wait(acc_full, 0);
+      ptx::tcgen05_fence_after();
+      ptx::tmem_ld64(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);
+      const int m = warp * 32 + lane;
+      float* slot = q.pblob + static_cast<int64_t>(blockIdx.x) * q.total;
+      float* dstp = nullptr;
+      int ncols = 0;
+      if (m < 64 * KB && m < a.w_rows) {
+        dstp = slot + q.dw_off + static_cast<int64_t>(m) * a.ldw + nb * 64;
+        ncols = a.w_cols - nb * 64;
+      } else if (ones && m == 64) {
+        dstp = slot + q.db_off + nb * 64;
+        ncols = a.w_cols - nb * 64;
+      }
+      if (dstp != nullptr) {
+        ncols = ncols > 64 ? 64 : ncols;
+        if ((ncols & 3) == 0 && (reinterpret_cast<uintptr_t>(dstp) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (4 * j < ncols) {
+              float4 o = reinterpret_cast<float4*>(dstp)[j];
+              o.x += v[4 * j]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
+              reinterpret_cast<float4*>(dstp)[j] = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < ncols) dstp[j] += v[j];
+        }
+      }
+    }
+  } else {
+    // ---- MMA issuer ----------------------------------------------------------------------------------------
+    constexpr uint32_t IDESC = umma_idesc_bf16_mn(128, 64);
+    for (int n = 0; n < ntiles; ++n) {
+      const int st = n & 1, use = n >> 1;
+      ptx::mbar_wait(&full[st], use & 1);
+      ptx::tcgen05_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t xs = ptx::smem_u32(smem + st * XT2_STAGE), ys = xs + 4 * PLANE_BYTES;
+        // MN-major: LBO = 128 (next 8 rows), SBO = 2048 (next 8 columns)
+        const uint64_t ad = ptx::umma_desc_k_nosw(xs, 128, 2048);
+        const uint64_t bd = ptx::umma_desc_k_nosw(ys, 128, 2048);
+        const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};          // (X plane, dY plane): lo.hi, hi.lo, hi.hi
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            ptx::umma_bf16_ss(tmem, ad + ((pa_[cb] * 2 * PLANE_BYTES + k * 256) >> 4),
+                              bd + ((pb_[cb] * PLANE_BYTES + k * 256) >> 4), IDESC, (n | cb | k) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[st]);
+        if (n == ntiles - 1) ptx::umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 8) ptx::tmem_dealloc(tmem, 64);
+}
+
+// grads[i] += sum over the slots of the per-CTA partial gradients, in slot order
+__global__ void __launch_bounds__(256) grad_partial_reduce_kernel(const float* __restrict__ pblob, int slots, int64_t total,
+                                                                  float* __restrict__ grads) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  int b = 0;
+  for (; b + 4 <= slots; b += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s4[j] += pblob[static_cast<int64_t>(b + j) * total + i];
+  }
+  for (; b < slots; ++b) s4[b & 3] += pblob[static_cast<int64_t>(b) * total + i];
+  grads[i] += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+}
+
+}  // namespace tspgnn

@@ -17,6 +17,7 @@
 #include "tc_kernels.cuh"
 #include "tc_fused.cuh"
 #include "train_kernels.cuh"
+#include "tc_train.cuh"
 #include "generic_kernels.cuh"
 
 using namespace tspgnn;
@@ -146,6 +147,10 @@ struct tspgnn_ctx {
   uint8_t* d_wm_pair[2] = {nullptr, nullptr};         // [0] V_msg_E, [1] E_msg_V:      [rank][layer][plane] x 4 KB
   float *mV2 = nullptr, *xV2 = nullptr;               // second halves of the message double buffers
   unsigned int* d_gridctr = nullptr;                  // grid barrier counter of the persistent fused kernel
+  bool train_tc = true;                               // reverse pass: tcgen05 row GEMMs (tensor-core modes); false: fp32 CUDA-core tiles
+  float* d_gpart = nullptr;                           // [gpart_slots][total] per-CTA partial gradients of tc_xtdy_kernel
+  int gpart_slots = 0;
+  float* cur_grads = nullptr;                         // gradient blob of the reverse pass in progress
   bool fused = false;                                 // tspgnn_step uses the persistent fused kernel (tensor-core modes);
                                                       // off by default: 6-10 % slower than the two-kernel sequence so far
   int dbg = 0;                                        // measurement aid of the fused kernel (FArgs::dbg; 4 = never any messages)
@@ -287,7 +292,7 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
     for (void* p : wp)
       if (p) cudaFree(p);
   }
-  void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2, h->d_gridctr, h->d_ent_row, h->d_ent_v};
+  void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2, h->d_gridctr, h->d_ent_row, h->d_ent_v, h->d_gpart};
   for (void* p : fp)
     if (p) cudaFree(p);
   void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg, h->d_lntab, h->d_biastab};
@@ -307,6 +312,7 @@ extern "C" int tspgnn_set_option(tspgnn_handle h, const char* name, double value
   if (!h || !name) return fail(TSPGNN_E_INVALID, "NULL handle or option name");
   const std::string key(name);
   if (key == "fused") h->fused = value != 0.0;
+  else if (key == "train_tc") h->train_tc = value != 0.0;
   else if (key == "v_pair_weight" && value > 0.0) h->v_pair_weight = value;
   else if (key == "dbg") h->dbg = static_cast<int>(value);
   else return fail(TSPGNN_E_INVALID, "unknown option '%s' (or bad value %g)", name, value);
