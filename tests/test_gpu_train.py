@@ -112,6 +112,46 @@ def test_gradients_match_oracle_config1():
     check_grads(blob, ref["grads"], GRAD_RTOL["bf16x3"], label="config1")
 
 
+@pytest.mark.parametrize("sizes,T", [([5, 12, 20, 7, 33, 9], 3), ([40] * 24, 4)])
+def test_tensor_core_reverse_pass_matches_fp32_reverse_pass(sizes, T):
+    """The tcgen05 reverse-pass GEMMs (csrc/tc_train.cuh: bf16x3 operands, MN-major X^T.dY, per-CTA partial
+    gradients summed in fixed order) against the fp32 CUDA-core kernels on the SAME forward state (bf16x3
+    mode, option train_tc = 1 / 0).  The recomputed activations carry the operands' 2^-16 relative error, so a
+    pre-activation within that distance of zero flips its ReLU mask like it does against the float64 oracle
+    (module docstring): gated are the cosine of the two blobs (>= 1 - 1e-5, measured 1 - 2e-6), the median per-tensor error
+    (<= 2e-3 of scale) and the worst tensor (<= 5e-2 of scale, the oracle gate of this mode; measured 2e-2).  On
+    IDENTICAL forward snapshots both reverse passes repeat to 3e-6 of scale (the residue: reductions in the incidence
+    products and the LayerNorm-parameter sums); between two training forwards the state differs by reduction order
+    (1e-7), which the fp32 recompute follows smoothly (5e-6) and the bf16x3 recompute in steps of its 2^-16
+    operand rounding (1e-4)."""
+    from tsp_gnn_b200.engine import Engine
+    EV, W, C, y, nv, ne = inst.synth_batch(sizes, seed=11)
+    params = orc.init_params(64, seed=5, perturb_ln=True)
+    blobs = []
+    for tc in (1, 0):
+        eng = Engine(64, "bf16x3", 0)
+        eng.set_params(params)
+        eng.set_option("train_tc", tc)
+        eng.plan(nv, ne, EV.src, EV.dst)
+        loss, logits, blob = run_backward(eng, W, C, y, T)
+        eng.close()
+        blobs.append(blob)
+    a, ref = (P.unflatten(x) for x in blobs)
+    cos = float(np.dot(blobs[0].astype(np.float64), blobs[1].astype(np.float64)) /
+                (np.linalg.norm(blobs[0].astype(np.float64)) * np.linalg.norm(blobs[1].astype(np.float64))))
+    assert cos >= 1.0 - 1e-5, cos
+    worst, rels = 0.0, []
+    for k, r in ref.items():
+        scale = float(np.abs(r).max())
+        err = float(np.abs(a[k] - r).max())
+        rels.append(err / (scale + 1e-30))
+        worst = max(worst, rels[-1])
+        assert err <= 5e-2 * scale + 1e-10, (k, err, scale)
+    print("cosine %.9f, median tensor error %.2e of scale" % (cos, float(np.median(rels))))
+    assert float(np.median(rels)) <= 2e-3
+    print("tensor-core vs fp32 reverse pass: worst tensor error %.2e of scale" % worst)
+
+
 @pytest.mark.parametrize("mode", ["simt", "bf16x3"])
 @pytest.mark.parametrize("name", ["ref_train_tiny", "ref_train_sparse"])
 def test_train_step_matches_reference_training_graph_fixtures(name, mode):
