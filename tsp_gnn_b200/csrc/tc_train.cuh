@@ -294,7 +294,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 // floating-point atomics, and no per-launch reduction (a last-CTA reduction of 32 partials cost 30 us per launch).
 // =====================================================================================================
 constexpr int XT2_THREADS = 288;
-constexpr int XT2_STAGE = 2 * 2 * PLANE_BYTES + 2 * PLANE_BYTES;   // X hi/lo (128 features) + dY hi/lo (64 columns) = 96 KB
 
 struct Xtdy2Args {
   XtdyArgs x;            // the contract of xtdy_kernel (dw / db are only used for their offsets, see below)
@@ -304,32 +303,45 @@ struct Xtdy2Args {
   int64_t dw_off, db_off;  // offsets of dW / db inside a slot (db_off < 0: no bias)
 };
 
+// SROWS rows per stage, NCH 8-column chunks of dY per CTA:
+//   <128, 8>  : 64 columns of dY per CTA (grid.y = 64-column blocks), 128-row stages -- the 64-wide MLP layers
+//   <64, 32>  : all 256 columns of dY in one CTA (one read of X instead of four, N = 256 MMAs at full rate),
+//               64-row stages -- the LSTM kernel gradient dK += [x, h]^T . dz
+// Either way a stage is X hi/lo (128 features) + dY hi/lo = 96 KB, two stages.
+template <int SROWS, int NCH>
 struct XT2Smem {
-  static constexpr int BAR_OFF = 2 * XT2_STAGE;
+  static constexpr int CS = SROWS * 16;                  // bytes between 8-column chunks of an image
+  static constexpr int XP = 16 * CS;                     // one bf16 plane of the X image (128 features)
+  static constexpr int YP = NCH * CS;                    // one bf16 plane of the dY image
+  static constexpr int STAGE = 2 * XP + 2 * YP;
+  static constexpr int BAR_OFF = 2 * STAGE;
   static constexpr int TOTAL = BAR_OFF + 8 * 5 + 16;
   static constexpr int DYN_BYTES = TOTAL + 128;
+  static_assert(DYN_BYTES <= 232448, "xtdy: shared memory budget (227 KB)");
 };
-static_assert(XT2Smem::DYN_BYTES <= 232448, "xtdy: shared memory budget (227 KB)");
 
 // kind::f16 instruction descriptor, bf16 A / B, fp32 D, BOTH operands MN-major (bits 15 / 16)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) {
   return ptx::umma_idesc_bf16(m, n) | (1u << 15) | (1u << 16);
 }
 
+template <int SROWS, int NCH>
 __global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args q) {
+  using L = XT2Smem<SROWS, NCH>;
+  constexpr int NCOLS = NCH * 8;
   const XtdyArgs& a = q.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + XT2Smem::BAR_OFF);   // [2]
-  uint64_t* empty = full + 2;                                              // [2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);   // [2]
+  uint64_t* empty = full + 2;                                        // [2]
   uint64_t* acc_full = empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nb = blockIdx.y;
+  const int col0 = blockIdx.y * NCOLS;                  // first column of dY / dW of this CTA
   const int KB = q.kblocks;
   const bool ones = (a.db != nullptr) && KB == 1;      // bias gradient through the all-ones feature 64
-  const int n_tiles_all = static_cast<int>((a.n_rows + TILE_ROWS - 1) / TILE_ROWS);
+  const int n_tiles_all = static_cast<int>((a.n_rows + SROWS - 1) / SROWS);
   int t0, t1;
   tile_range(blockIdx.x, gridDim.x, n_tiles_all, t0, t1);
   const int ntiles = t1 - t0;
@@ -342,9 +354,9 @@ __global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args
     ptx::mbar_init(acc_full, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 8) ptx::tmem_alloc(tmem_slot, 64);
+  if (warp == 8) ptx::tmem_alloc(tmem_slot, NCOLS);
   // feature chunks the producers never write (X has 64 or 128 features, M is always 128) must read as zero
-  for (int i = tid; i < 2 * XT2_STAGE / 16; i += XT2_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 2 * L::STAGE / 16; i += XT2_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   ptx::fence_proxy_async_smem();
   ptx::tcgen05_fence_before();
   __syncthreads();
@@ -356,14 +368,13 @@ __global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args
     // a warp task = 8 rows x 4 chunks of 8 columns (lane -> row lane & 7, chunk lane >> 3): every lane reads 32
     // contiguous bytes, every quarter-warp writes 128 contiguous bytes of an operand plane
     const int r8 = lane & 7, cq = lane >> 3;
-    const int quads = 2 * KB + 2;                       // chunk quads per row group: X (2 per 64 columns), dY (2)
-    const int ntask = 16 * quads;
-    const float* dyp = a.dy + nb * 64;
+    const int quads = 2 * KB + NCH / 4;                 // chunk quads per row group: X (2 per 64 columns), dY
+    const int ntask = (SROWS / 8) * quads;
+    const float* dyp = a.dy + col0;
     for (int n = 0; n < ntiles; ++n) {
       const int st = n & 1, use = n >> 1;
-      const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
-      uint8_t* stage = smem + st * XT2_STAGE;
-      const uint32_t xs = ptx::smem_u32(stage), ys = xs + 4 * PLANE_BYTES;
+      const int64_t row0 = static_cast<int64_t>(t0 + n) * SROWS;
+      const uint32_t xs = ptx::smem_u32(smem + st * L::STAGE), ys = xs + 2 * L::XP;
       if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
 #pragma unroll 1
       for (int tb = warp; tb < ntask; tb += 64) {       // eight tasks (sixteen 16-byte loads) in flight per lane
@@ -381,11 +392,11 @@ __global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args
             if (qd < 2 * KB) {
               const int kb = qd >> 1, chunk = (qd & 1) * 4 + cq;           // chunk inside the 64-column block
               p = (kb == 0 ? a.x[0] : a.x[1]) + row * (kb == 0 ? a.xld[0] : a.xld[1]) + chunk * 8;
-              dst[i] = xs + (kb * 8 + chunk) * 2048 + (g * 8 + r8) * 16;
+              dst[i] = xs + (kb * 8 + chunk) * L::CS + (g * 8 + r8) * 16;
             } else {
               const int chunk = (qd - 2 * KB) * 4 + cq;
               p = dyp + row * a.dyld + chunk * 8;
-              dst[i] = ys + chunk * 2048 + (g * 8 + r8) * 16;
+              dst[i] = ys + chunk * L::CS + (g * 8 + r8) * 16;
             }
             if (row < a.n_rows) {
               u[i][0] = reinterpret_cast<const float4*>(p)[0];
@@ -401,74 +412,73 @@ __global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args
             split8(x, hi, lo);
             const bool is_x = dst[i] < ys;
             ptx::sts128(dst[i], hi);
-            ptx::sts128(dst[i] + (is_x ? 2 * PLANE_BYTES : PLANE_BYTES), lo);
+            ptx::sts128(dst[i] + (is_x ? L::XP : L::YP), lo);
           }
         }
       }
-      if (ones && warp < 4) {
+      if (ones && warp < SROWS / 32) {
         // feature 64 (chunk 8, element 0) = 1 for the valid rows of the tile: its row of D is colsum(dY)
         const int r = warp * 32 + lane;
         const uint32_t one = (row0 + r < a.n_rows) ? 0x3F80u : 0u;       // bf16(1.0) in the low half
-        ptx::sts128(xs + 8 * 2048 + r * 16, make_uint4(one, 0u, 0u, 0u));
+        ptx::sts128(xs + 8 * L::CS + r * 16, make_uint4(one, 0u, 0u, 0u));
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full[st]);
     }
-    // ---- partial of this CTA: lane = feature, 64 columns, added to this CTA's slot ------------------------------
+    // ---- partial of this CTA: lane = feature, NCOLS columns, added to this CTA's slot ---------------------------
     if (warp < 4 && ntiles > 0) {
-      float v[64];
       ptx::mbar_wait(acc_full, 0);
       ptx::tcgen05_fence_after();
-      ptx::tmem_ld64(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);
       const int m = warp * 32 + lane;
       float* slot = q.pblob + static_cast<int64_t>(blockIdx.x) * q.total;
-      float* dstp = nullptr;
-      int ncols = 0;
-      if (m < 64 * KB && m < a.w_rows) {
-        dstp = slot + q.dw_off + static_cast<int64_t>(m) * a.ldw + nb * 64;
-        ncols = a.w_cols - nb * 64;
-      } else if (ones && m == 64) {
-        dstp = slot + q.db_off + nb * 64;
-        ncols = a.w_cols - nb * 64;
-      }
-      if (dstp != nullptr) {
+#pragma unroll 1
+      for (int cb = 0; cb < NCOLS / 64; ++cb) {
+        float v[64];
+        ptx::tmem_ld64(tmem + (static_cast<uint32_t>(warp * 32) << 16) + cb * 64, v);
+        const int c0 = col0 + cb * 64;
+        float* dstp = nullptr;
+        if (m < 64 * KB && m < a.w_rows) dstp = slot + q.dw_off + static_cast<int64_t>(m) * a.ldw + c0;
+        else if (ones && m == 64) dstp = slot + q.db_off + c0;
+        int ncols = a.w_cols - c0;
         ncols = ncols > 64 ? 64 : ncols;
-        if ((ncols & 3) == 0 && (reinterpret_cast<uintptr_t>(dstp) & 15) == 0) {
+        if (dstp != nullptr && ncols > 0) {
+          if ((ncols & 3) == 0 && (reinterpret_cast<uintptr_t>(dstp) & 15) == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (4 * j < ncols) {
-              float4 o = reinterpret_cast<float4*>(dstp)[j];
-              o.x += v[4 * j]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
-              reinterpret_cast<float4*>(dstp)[j] = o;
+            for (int j = 0; j < 16; ++j) {
+              if (4 * j < ncols) {
+                float4 o = reinterpret_cast<float4*>(dstp)[j];
+                o.x += v[4 * j]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
+                reinterpret_cast<float4*>(dstp)[j] = o;
+              }
             }
-          }
-        } else {
+          } else {
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (j < ncols) dstp[j] += v[j];
+            for (int j = 0; j < 64; ++j)
+              if (j < ncols) dstp[j] += v[j];
+          }
         }
       }
     }
   } else {
     // ---- MMA issuer ----------------------------------------------------------------------------------------
-    constexpr uint32_t IDESC = umma_idesc_bf16_mn(128, 64);
+    constexpr uint32_t IDESC = umma_idesc_bf16_mn(128, NCOLS);
     for (int n = 0; n < ntiles; ++n) {
       const int st = n & 1, use = n >> 1;
       ptx::mbar_wait(&full[st], use & 1);
       ptx::tcgen05_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t xs = ptx::smem_u32(smem + st * XT2_STAGE), ys = xs + 4 * PLANE_BYTES;
-        // MN-major: LBO = 128 (next 8 rows), SBO = 2048 (next 8 columns)
-        const uint64_t ad = ptx::umma_desc_k_nosw(xs, 128, 2048);
-        const uint64_t bd = ptx::umma_desc_k_nosw(ys, 128, 2048);
+        const uint32_t xs = ptx::smem_u32(smem + st * L::STAGE), ys = xs + 2 * L::XP;
+        // MN-major: LBO = 128 (next 8 rows), SBO = chunk stride (next 8 columns)
+        const uint64_t ad = ptx::umma_desc_k_nosw(xs, 128, L::CS);
+        const uint64_t bd = ptx::umma_desc_k_nosw(ys, 128, L::CS);
         const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};          // (X plane, dY plane): lo.hi, hi.lo, hi.hi
 #pragma unroll
         for (int cb = 0; cb < 3; ++cb) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            ptx::umma_bf16_ss(tmem, ad + ((pa_[cb] * 2 * PLANE_BYTES + k * 256) >> 4),
-                              bd + ((pb_[cb] * PLANE_BYTES + k * 256) >> 4), IDESC, (n | cb | k) ? 1u : 0u);
+          for (int k = 0; k < SROWS / 16; ++k)
+            ptx::umma_bf16_ss(tmem, ad + ((pa_[cb] * L::XP + k * 256) >> 4), bd + ((pb_[cb] * L::YP + k * 256) >> 4), IDESC,
+                              (n | cb | k) ? 1u : 0u);
         }
         ptx::umma_commit(&empty[st]);
         if (n == ntiles - 1) ptx::umma_commit(acc_full);
@@ -478,7 +488,7 @@ __global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args
   }
   ptx::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) ptx::tmem_dealloc(tmem, 64);
+  if (warp == 8) ptx::tmem_dealloc(tmem, NCOLS);
 }
 
 // grads[i] += sum over the slots of the per-CTA partial gradients, in slot order

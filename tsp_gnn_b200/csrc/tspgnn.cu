@@ -152,6 +152,16 @@ struct tspgnn_ctx {
   float* d_gpart = nullptr;                           // [gpart_slots][total] per-CTA partial gradients of tc_xtdy_kernel
   int gpart_slots = 0;
   float* cur_grads = nullptr;                         // gradient blob of the reverse pass in progress
+  struct BwdKey {                                     // what a captured reverse-pass graph bakes in
+    int64_t plan_generation;
+    int T;
+    const void *G, *y, *loss;
+    int global_batch, train_tc;
+  };
+  BwdKey bwd_key = {};
+  cudaGraphExec_t bwd_exec = nullptr;
+  int64_t bwd_launches = 0;
+  bool bwd_key_valid = false, bwd_graphs = true;      // option "train_graph"
   bool fused = false;                                 // tspgnn_step uses the persistent fused kernel (tensor-core modes);
                                                       // off by default: 6-10 % slower than the two-kernel sequence so far
   int dbg = 0;                                        // measurement aid of the fused kernel (FArgs::dbg; 4 = never any messages)
@@ -199,6 +209,11 @@ static tspgnn_ctx* g_const_owner = nullptr;
 static void drop_graphs(tspgnn_ctx* h) {
   for (auto& kv : h->step_graphs) cudaGraphExecDestroy(kv.second);
   h->step_graphs.clear();
+  if (h->bwd_exec) {
+    cudaGraphExecDestroy(h->bwd_exec);
+    h->bwd_exec = nullptr;
+  }
+  h->bwd_key_valid = false;
 }
 
 static int upload_constants(tspgnn_ctx* h, cudaStream_t s) {
@@ -314,6 +329,7 @@ extern "C" int tspgnn_set_option(tspgnn_handle h, const char* name, double value
   const std::string key(name);
   if (key == "fused") h->fused = value != 0.0;
   else if (key == "train_tc") h->train_tc = value != 0.0;
+  else if (key == "train_graph") h->bwd_graphs = value != 0.0;
   else if (key == "v_pair_weight" && value > 0.0) h->v_pair_weight = value;
   else if (key == "dbg") h->dbg = static_cast<int>(value);
   else return fail(TSPGNN_E_INVALID, "unknown option '%s' (or bad value %g)", name, value);
