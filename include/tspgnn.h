@@ -53,10 +53,13 @@ int tspgnn_create(int d, int mode, int device, tspgnn_handle* out);
 int tspgnn_destroy(tspgnn_handle h);
 int tspgnn_get_mode(tspgnn_handle h);
 
-/* Tuning / diagnosis knobs (no equivalent in the reference).  "fused" (default 1): tspgnn_step runs one
- * fused CTA-pair kernel per timestep (tensor-core modes); 0 selects the two-kernel sequence (message MLPs,
- * then LSTM cells), which computes the same thing.  "v_pair_weight": relative cost of a vertex tile pair
- * used to split the clusters of the fused kernel between edge and vertex tiles. */
+/* Tuning / diagnosis knobs (no equivalent in the reference).
+ *   "fused" (default 0): 1 = tspgnn_step runs the persistent fused CTA-pair kernel (tensor-core modes) instead of
+ *       the two-kernel sequence (message MLPs, then LSTM cells); both compute the same thing.
+ *   "v_pair_weight": relative cost of a vertex tile pair used to split the clusters of the fused kernel.
+ *   "train_tc" (default 1): reverse-pass contractions on tcgen05 (tensor-core modes); 0 = fp32 CUDA-core kernels.
+ *   "train_graph" (default 1): replay the reverse pass from a CUDA graph once the same tspgnn_backward call
+ *       (same plan geometry, buffers and timestep count) has been seen twice in a row. */
 int tspgnn_set_option(tspgnn_handle h, const char* name, double value);
 
 /* Replaces tf.global_variables_initializer() / Saver.restore (train.py:210, util.py:17):

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtspgnn.so")
 SOURCES = ["tspgnn.cu"]
-HEADERS = ["common.cuh", "simt_kernels.cuh", "tc_ptx.cuh", "tc_kernels.cuh", "tc_fused.cuh", "train_kernels.cuh", "generic_kernels.cuh", "train_host.inc"]
+HEADERS = ["common.cuh", "simt_kernels.cuh", "tc_ptx.cuh", "tc_kernels.cuh", "tc_fused.cuh", "train_kernels.cuh", "tc_train.cuh", "generic_kernels.cuh", "train_host.inc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false",
