@@ -506,4 +506,266 @@ __global__ void __launch_bounds__(256) grad_partial_reduce_kernel(const float* _
   grads[i] += (s4[0] + s4[1]) + (s4[2] + s4[3]);
 }
 
+
+// =====================================================================================================
+// One layer of an MLP's reverse chain in ONE kernel (mlp_reverse):
+//   dW_l += a_{l-1}^T . d_l,  db_l += colsum(d_l)          (tc_xtdy_kernel's contract)
+//   d_{l-1} = (d_l . W_l^T) * (a_{l-1} > 0)                 (tc_rowgemm_kernel<1,1,TRANS,MASK>; l = 0: plain or +=)
+// Both products consume the SAME shared-memory image of the d_l tile: as the K-major A operand of d_l . W_l^T
+// (M = rows, K = output features) and as the MN-major B operand of a^T . d_l (N = output features, K = rows);
+// a_{l-1} is read once, as the MN-major A operand image and (fp32, from L2) as the ReLU mask.  Against the two
+// separate kernels a layer moves 77 MB instead of 128 MB at the north-star size and costs one launch.
+// 416 threads: warps 0-3 epilogue (d_{l-1} tile; at the end the CTA's weight-gradient partial), warps 4-11
+// producers, warp 12 MMA issuer.  TMEM: two 64-column accumulators for d_l . W^T and one for a^T . d_l.
+// =====================================================================================================
+constexpr int LR_THREADS = 416;
+
+struct LayerRevArgs {
+  const float* d;        // d_l [rows, 64], leading dimension dld
+  int dld;
+  const float* a;        // a_{l-1} [rows, 64]: input of layer l
+  int ald;
+  float* y;              // d_{l-1} [rows, 64]
+  int yld;
+  const float* w;        // W_l stored [w_rows = inputs][w_cols = outputs], leading dimension ldw
+  int ldw, w_rows, w_cols;
+  float* pblob;          // per-CTA partial gradients (see tc_xtdy_kernel)
+  int64_t total, dw_off, db_off;
+  int64_t n_rows;
+};
+
+struct LRSmem {
+  static constexpr int W_BYTES = 2 * 64 * 128;                       // W^T image, hi + lo
+  static constexpr int DP = PLANE_BYTES;                             // one plane of the d image (64 columns)
+  static constexpr int AP = 2 * PLANE_BYTES;                         // one plane of the a image (128 features: 64 + ones + zeros)
+  static constexpr int STAGE = 2 * DP + 2 * AP;                      // 96 KB
+  static constexpr int STAGE_OFF = W_BYTES;
+  static constexpr int BAR_OFF = STAGE_OFF + 2 * STAGE;
+  static constexpr int TOTAL = BAR_OFF + 8 * 9 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 128;
+};
+static_assert(LRSmem::DYN_BYTES <= 232448, "layer reverse: shared memory budget (227 KB)");
+
+template <int EPI>
+__global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const LayerRevArgs a) {
+  using L = LRSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* wsm = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);   // [2] stage filled (8 producer warps)
+  uint64_t* empty = full + 2;                                        // [2] stage consumed (MMA commit)
+  uint64_t* d1_full = empty + 2;                                     // [2] d_l . W^T of a tile complete
+  uint64_t* d1_empty = d1_full + 2;                                  // [2] its accumulator drained (4 epilogue warps)
+  uint64_t* d2_full = d1_empty + 2;                                  // a^T . d_l of all tiles complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool ones = a.db_off >= 0;
+  const int n_tiles_all = static_cast<int>((a.n_rows + TILE_ROWS - 1) / TILE_ROWS);
+  int t0, t1;
+  tile_range(blockIdx.x, gridDim.x, n_tiles_all, t0, t1);
+  const int ntiles = t1 - t0;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&full[s], 8);
+      ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&d1_full[s], 1);
+      ptx::mbar_init(&d1_empty[s], 4);
+    }
+    ptx::mbar_init(d2_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 12) ptx::tmem_alloc(tmem_slot, 256);
+  // the a-image chunks the producers never write (features 72..127) must read as zero
+  for (int i = tid; i < 2 * L::STAGE / 16; i += LR_THREADS)
+    reinterpret_cast<uint4*>(smem + L::STAGE_OFF)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // B operand of d_l . W^T: image[n = input i][k = output o] = W[i][o]
+  for (int i = tid; i < 8 * 64; i += LR_THREADS) {
+    const int n = i & 63, kc = i >> 6;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kc * 8 + j;
+      v[j] = (n < a.w_rows && k < a.w_cols) ? __ldg(a.w + static_cast<int64_t>(n) * a.ldw + k) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    uint8_t* p = wsm + kc * (64 * 16) + n * 16;
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + 64 * 128) = lo;
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ---- epilogue: d_{l-1} tile ---------------------------------------------------------------------------------
+    const int tq0 = lane & 3, tq1 = lane >> 2;
+    for (int n = 0; n < ntiles; ++n) {
+      const int acc = n & 1, use = n >> 1;
+      const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS + warp * 32 + tq1;   // + 8 m
+      float2 pre[4][8];           // ReLU mask source a_{l-1} (MASK) or the previous output (ACCUM), before the wait
+      if (EPI & (EPI_MASK | EPI_ACCUM)) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int64_t row = row0 + 8 * m;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            pre[m][k] = make_float2(0.f, 0.f);
+            if (row < a.n_rows) {
+              const float* src = (EPI & EPI_MASK) ? a.a + row * a.ald : a.y + row * a.yld;
+              pre[m][k] = *reinterpret_cast<const float2*>(src + 2 * tq0 + 8 * k);
+            }
+          }
+        }
+      }
+      ptx::mbar_wait(&d1_full[acc], use & 1);
+      ptx::tcgen05_fence_after();
+      float qa[32], qb[32];
+      ptx::tmem_ld_quad64(tmem + (static_cast<uint32_t>(warp * 32) << 16) + acc * 64, qa, qb);
+      ptx::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&d1_empty[acc]);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int64_t row = row0 + 8 * m;
+        if (row < a.n_rows) {
+          float* yr = a.y + row * a.yld + 2 * tq0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int ix = 4 * k + 2 * (m & 1);
+            float2 v = make_float2(((m < 2) ? qa : qb)[ix], ((m < 2) ? qa : qb)[ix + 1]);
+            if (EPI & EPI_MASK) {
+              v.x = (pre[m][k].x > 0.f) ? v.x : 0.f;
+              v.y = (pre[m][k].y > 0.f) ? v.y : 0.f;
+            }
+            if (EPI & EPI_ACCUM) {
+              v.x += pre[m][k].x;
+              v.y += pre[m][k].y;
+            }
+            *reinterpret_cast<float2*>(yr + 8 * k) = v;
+          }
+        }
+      }
+    }
+    // ---- the CTA's weight-gradient partial: lane = input feature, 64 output columns ---------------------------------
+    if (ntiles > 0) {
+      ptx::mbar_wait(d2_full, 0);
+      ptx::tcgen05_fence_after();
+      float v[64];
+      ptx::tmem_ld64(tmem + (static_cast<uint32_t>(warp * 32) << 16) + 128, v);
+      const int m = warp * 32 + lane;
+      float* slot = a.pblob + static_cast<int64_t>(blockIdx.x) * a.total;
+      float* dstp = nullptr;
+      if (m < 64 && m < a.w_rows) dstp = slot + a.dw_off + static_cast<int64_t>(m) * a.ldw;
+      else if (ones && m == 64) dstp = slot + a.db_off;
+      const int ncols = a.w_cols > 64 ? 64 : a.w_cols;
+      if (dstp != nullptr) {
+        if ((ncols & 3) == 0 && (reinterpret_cast<uintptr_t>(dstp) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (4 * j < ncols) {
+              float4 o = reinterpret_cast<float4*>(dstp)[j];
+              o.x += v[4 * j]; o.y += v[4 * j + 1]; o.z += v[4 * j + 2]; o.w += v[4 * j + 3];
+              reinterpret_cast<float4*>(dstp)[j] = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (j < ncols) dstp[j] += v[j];
+        }
+      }
+    }
+  } else if (warp < 12) {
+    // ---- producers: d_l and a_{l-1} tiles -> bf16 hi / lo images ----------------------------------------------------
+    const int pw = warp - 4;
+    const int r8 = lane & 7, cq = lane >> 3;
+    constexpr int quads = 4, ntask = 16 * quads;          // per 8-row group: d (2 quads of 4 chunks), a (2)
+    for (int n = 0; n < ntiles; ++n) {
+      const int st = n & 1, use = n >> 1;
+      const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
+      const uint32_t ds = ptx::smem_u32(smem + L::STAGE_OFF + st * L::STAGE), as = ds + 2 * L::DP;
+      // the tile's sixteen 16-byte loads per lane are requested before the stage is waited for
+      float4 u[8][2];
+      uint32_t dst[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int task = pw + 8 * i;
+        const int g = task / quads, qd = task % quads;
+        const int64_t row = row0 + g * 8 + r8;
+        const int chunk = (qd & 1) * 4 + cq;
+        const float* p = (qd < 2) ? a.d + row * a.dld + chunk * 8 : a.a + row * a.ald + chunk * 8;
+        dst[i] = ((qd < 2) ? ds : as) + chunk * 2048 + (g * 8 + r8) * 16;
+        u[i][0] = u[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < a.n_rows) {
+          u[i][0] = reinterpret_cast<const float4*>(p)[0];
+          u[i][1] = reinterpret_cast<const float4*>(p)[1];
+        }
+      }
+      static_assert(ntask == 64, "eight producer warps, eight tasks each");
+      if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const bool is_d = dst[i] < as;
+        ptx::sts128(dst[i], hi);
+        ptx::sts128(dst[i] + (is_d ? L::DP : L::AP), lo);
+      }
+      if (ones && pw < 4) {       // feature 64 of the a image = 1 for the valid rows: its row of a^T . d_l is colsum(d_l)
+        const int r = pw * 32 + lane;
+        const uint32_t one = (row0 + r < a.n_rows) ? 0x3F80u : 0u;
+        ptx::sts128(as + 8 * 2048 + r * 16, make_uint4(one, 0u, 0u, 0u));
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full[st]);
+    }
+  } else {
+    // ---- MMA issuer -----------------------------------------------------------------------------------------------
+    constexpr uint32_t IDESC1 = ptx::umma_idesc_bf16(128, 64);        // d_l . W^T: both K-major
+    constexpr uint32_t IDESC2 = umma_idesc_bf16_mn(128, 64);          // a^T . d_l: both MN-major
+    const uint64_t wdesc = ptx::umma_desc_k_nosw(ptx::smem_u32(wsm), 64 * 16, 128);
+    for (int n = 0; n < ntiles; ++n) {
+      const int st = n & 1, use = n >> 1;
+      ptx::mbar_wait(&full[st], use & 1);
+      if (use >= 1) ptx::mbar_wait(&d1_empty[st], (use - 1) & 1);
+      ptx::tcgen05_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ds = ptx::smem_u32(smem + L::STAGE_OFF + st * L::STAGE), as = ds + 2 * L::DP;
+        const uint64_t dk = ptx::umma_desc_k_nosw(ds, 2048, 128);     // d image as K-major A (rows x outputs)
+        const uint64_t dmn = ptx::umma_desc_k_nosw(ds, 128, 2048);    // d image as MN-major B (outputs x rows)
+        const uint64_t amn = ptx::umma_desc_k_nosw(as, 128, 2048);    // a image as MN-major A (inputs x rows)
+        const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16_ss(tmem + st * 64, dk + ((pa_[cb] * L::DP + k * 4096) >> 4),
+                              wdesc + ((pb_[cb] * (64 * 128) + k * (2 * 64 * 16)) >> 4), IDESC1, (cb | k) ? 1u : 0u);
+        }
+        ptx::umma_commit(&d1_full[st]);
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            ptx::umma_bf16_ss(tmem + 128, amn + ((pa_[cb] * L::AP + k * 256) >> 4), dmn + ((pb_[cb] * L::DP + k * 256) >> 4),
+                              IDESC2, (n | cb | k) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[st]);
+        if (n == ntiles - 1) ptx::umma_commit(d2_full);
+      }
+      __syncwarp();
+    }
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 12) ptx::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace tspgnn
