@@ -20,7 +20,7 @@
 #include "../../tsp_gnn_b200/csrc/tc_ptx.cuh"
 using namespace tspgnn;
 
-enum Role : int { IDLE = 0, M256, M64, LDSD, LDSB, STSD, TLD, TST, LDG, FMA, M64SW, M64TS, M256TS, LDCU, LDSB64, M128, M64MN, NROLE };
+enum Role : int { IDLE = 0, M256, M64, LDSD, LDSB, STSD, TLD, TST, LDG, FMA, M64SW, M64TS, M256TS, LDCU, LDSB64, M128, M64MN, M256MN, NROLE };
 __constant__ float2 c_tab[1024];
 struct Cfg { int role[16]; long long window; };
 
@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(512, 1) pipe_kernel(Cfg cfg, const float* __re
       ops += 4;
     }
 
-  } else if (role == M64SW || role == M64TS || role == M256TS || role == M128 || role == M64MN) {
-    const int N = (role == M256TS) ? 256 : (role == M128 ? 128 : 64);
+  } else if (role == M64SW || role == M64TS || role == M256TS || role == M128 || role == M64MN || role == M256MN) {
+    const int N = (role == M256TS || role == M256MN) ? 256 : (role == M128 ? 128 : 64);
     const uint32_t idesc = (N == 256) ? ptx::umma_idesc_bf16(128, 256) : (N == 128 ? ptx::umma_idesc_bf16(128, 128) : ptx::umma_idesc_bf16(128, 64));
     uint64_t adesc, bdesc;
     uint32_t kstepA, kstepB;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(512, 1) pipe_kernel(Cfg cfg, const float* __re
       kstepB = (2 * N * 16) >> 4;
     }
     uint32_t idesc2 = idesc;
-    if (role == M64MN) {      // both operands MN-major: the chunk-major image read as [col][row]
+    if (role == M64MN || role == M256MN) {      // both operands MN-major: the chunk-major image read as [col][row]
       adesc = ptx::umma_desc_k_nosw(ptx::smem_u32(a_sm), 128, 2048);
       bdesc = ptx::umma_desc_k_nosw(ptx::smem_u32(b_sm), 128, 2048);
       kstepA = kstepB = 256 >> 4;
@@ -235,11 +235,12 @@ __global__ void __launch_bounds__(512, 1) pipe_kernel(Cfg cfg, const float* __re
   if (warp == 0) ptx::tmem_dealloc(tmem, 512);
 }
 
-static const char* rname[] = {"idle", "M256", "M64", "LDSD", "LDSB", "STSD", "TLD", "TST", "LDG", "FMA", "M64SW", "M64TS", "M256TS", "LDCU", "LDSB64", "M128", "M64MN"};
+static const char* rname[] = {"idle", "M256", "M64", "LDSD", "LDSB", "STSD", "TLD", "TST", "LDG", "FMA", "M64SW", "M64TS", "M256TS", "LDCU", "LDSB64", "M128", "M64MN", "M256MN"};
 static double bytes_per_op(int r) {
   switch (r) {
     case M256: return 4096 + 8192;
     case M64: case M64SW: case M64MN: return 4096 + 2048;
+    case M256MN: return 4096 + 8192;
     case M64TS: return 2048;
     case M256TS: return 8192;
     case M128: return 8192;
@@ -267,7 +268,8 @@ int main() {
   std::vector<Sc> scs = {
       {"mma N64 K-major alone", {{M64, 1}}},
       {"mma N64 MN-major alone", {{M64MN, 1}}},
-      {"mma N64 MN-major + sts x8", {{M64MN, 1}, {IDLE, 3}, {STSD, 8}}},
+      {"mma N256 MN-major alone", {{M256MN, 1}}},
+      {"mma N256 MN-major + sts x8", {{M256MN, 1}, {IDLE, 3}, {STSD, 8}}},
   };
   for (auto& sc : scs) {
     Cfg cfg;

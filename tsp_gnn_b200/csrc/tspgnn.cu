@@ -151,6 +151,7 @@ struct tspgnn_ctx {
   bool train_tc = true;                               // reverse pass: tcgen05 row GEMMs (tensor-core modes); false: fp32 CUDA-core tiles
   float* d_gpart = nullptr;                           // [gpart_slots][total] per-CTA partial gradients of tc_xtdy_kernel
   int gpart_slots = 0;
+  int64_t gpart_stride = 0;                           // floats between slots (blob size rounded up to 32)
   float* cur_grads = nullptr;                         // gradient blob of the reverse pass in progress
   struct BwdKey {                                     // what a captured reverse-pass graph bakes in
     int64_t plan_generation;
