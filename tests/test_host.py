@@ -119,8 +119,11 @@ def test_build_network_key_set():
     for k in ("gnn", "route_exists", "n_vertices", "n_edges", "EV", "W", "C", "time_steps", "last_states",
               "predictions", "TP", "FP", "TN", "FN", "acc", "loss", "train_step"):       # model.py:97-104,123,147-167
         assert k in GNN
-    with pytest.raises(NotImplementedError):
-        tg.build_network(32)["gnn"]
+    # other embedding sizes (train.py:108 -d) build too: they run on the generic CUDA path behind Session.run
+    assert tg.build_network(32)["gnn"]._kernel_roles is None
+    assert tg.build_network(64)["gnn"]._kernel_roles is not None
+    with pytest.raises(ValueError):
+        tg.build_network(4)
 
 
 def test_graph_file_roundtrip_and_loader(tmp_path):

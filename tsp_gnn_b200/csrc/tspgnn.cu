@@ -108,8 +108,8 @@ float bf16_to_f(uint16_t h) {
 // output feature n, k-value k at wimg_off(n, k, nrows) -- the un-swizzled K-major layout the
 // kernels describe with LBO = nrows*16, SBO = 128.
 void make_b_image(const float* W, int ldw, int k0, int n0, int nrows, int plane, uint8_t* img) {
-  for (int n = 0; n < nrows; ++n)
-    for (int k = 0; k < 64; ++k) {
+  for (int k = 0; k < 64; ++k)          // k outermost: reads run along rows of W
+    for (int n = 0; n < nrows; ++n) {
       const float w = W[static_cast<int64_t>(k0 + k) * ldw + n0 + n];
       const uint16_t hi = bf16_rn(w);
       const uint16_t val = plane == 0 ? hi : bf16_rn(w - bf16_to_f(hi));
@@ -325,6 +325,8 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
 
 extern "C" int tspgnn_get_mode(tspgnn_handle h) { return h ? h->mode : TSPGNN_E_INVALID; }
 
+static int install_params(tspgnn_ctx* h, bool upload_blob);
+
 extern "C" int tspgnn_set_option(tspgnn_handle h, const char* name, double value) {
   if (!h || !name) return fail(TSPGNN_E_INVALID, "NULL handle or option name");
   const std::string key(name);
@@ -337,6 +339,7 @@ extern "C" int tspgnn_set_option(tspgnn_handle h, const char* name, double value
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   drop_graphs(h);      // the captured timestep graphs bake the launch sequence in
+  if (key == "fused" && h->fused && h->has_params) return install_params(h, false);   // the CTA-pair images
   return 0;
 }
 extern "C" int64_t tspgnn_sum_edges(tspgnn_handle h) { return h && h->has_plan ? h->nE : -1; }
@@ -454,16 +457,18 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
       const float* b4 = blob + o.msg_b[1][3];
       std::vector<double> row(4 * D);
       for (int k = 0; k <= 2 * D; ++k) {            // k == 2*D: the bias row
-        for (int n = 0; n < 4 * D; ++n) {
-          double acc = 0.0;
-          if (k < D) {
-            for (int j = 0; j < D; ++j) acc += static_cast<double>(W4[k * D + j]) * K[static_cast<int64_t>(j) * 4 * D + n];
-          } else if (k < 2 * D) {
-            acc = K[static_cast<int64_t>(k) * 4 * D + n];
-          } else {
-            for (int j = 0; j < D; ++j) acc += static_cast<double>(b4[j]) * K[static_cast<int64_t>(j) * 4 * D + n];
+        if (k >= D && k < 2 * D) {
+          for (int n = 0; n < 4 * D; ++n) row[n] = K[static_cast<int64_t>(k) * 4 * D + n];
+        } else {
+          // j outermost: the inner loop runs along a row of K (this runs after every optimizer step; with n
+          // outermost the strided walk down a column of K made it 2 ms).  Per n the terms still add up in j order.
+          const float* lhs = (k < D) ? W4 + k * D : b4;
+          for (int n = 0; n < 4 * D; ++n) row[n] = 0.0;
+          for (int j = 0; j < D; ++j) {
+            const double w = static_cast<double>(lhs[j]);
+            const float* Kj = K + static_cast<int64_t>(j) * 4 * D;
+            for (int n = 0; n < 4 * D; ++n) row[n] += w * Kj[n];
           }
-          row[n] = acc;
         }
         for (int g = 0; g < 4; ++g) {
           double m = 0.0;
@@ -493,8 +498,9 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
       CUDA_TRY(cudaMemcpy(h->d_wmlp[m], img.data(), img.size(), cudaMemcpyHostToDevice));
     }
     // Images of the fused CTA-pair kernel: CTA `rank` of a pair holds output features
-    // [rank * N/2, (rank + 1) * N/2) of every B operand (tcgen05.mma.cta_group::2).
-    for (int c = 0; c < 2; ++c) {
+    // [rank * N/2, (rank + 1) * N/2) of every B operand (tcgen05.mma.cta_group::2).  Built only while that
+    // kernel is selected (tspgnn_set_option "fused" re-installs): this runs after every optimizer step.
+    for (int c = 0; c < 2 && h->fused; ++c) {
       // c == 0: kc still holds the folded vertex kernel [W4.Kx ; Kh] built above; c == 1: centred E kernel
       if (c == 1)
         for (int k = 0; k < 2 * D; ++k)
@@ -513,7 +519,7 @@ static int install_params(tspgnn_ctx* h, bool upload_blob) {
       if (!h->d_wl_pair[c] && dev_alloc(&h->d_wl_pair[c], static_cast<int64_t>(img.size()))) return TSPGNN_E_CUDA;
       CUDA_TRY(cudaMemcpy(h->d_wl_pair[c], img.data(), img.size(), cudaMemcpyHostToDevice));
     }
-    for (int m = 0; m < 2; ++m) {
+    for (int m = 0; m < 2 && h->fused; ++m) {
       img.assign(static_cast<size_t>(2) * 4 * hp * 4096, 0);
       for (int r = 0; r < 2; ++r)
         for (int l = 0; l < 4; ++l)

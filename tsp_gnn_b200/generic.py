@@ -65,6 +65,19 @@ class CooMatrix(object):
         self.vals = None if np.all(vals == 1.0) else torch.from_numpy(vals).to(device)
         self.nnz = int(r.shape[0])
 
+    @classmethod
+    def from_entries(cls, rows, cols, vals, shape, device):
+        """The same object from the stored entries themselves (int rows / cols, vals None = all ones), for
+        matrices that are never held densely (the [sumE, sumV] incidence matrix of a large batch)."""
+        import torch
+        self = cls.__new__(cls)
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.int32)).to(device)
+        self.cols = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).to(device)
+        self.vals = None if vals is None else torch.from_numpy(np.ascontiguousarray(vals, dtype=np.float32)).to(device)
+        self.nnz = int(self.rows.shape[0])
+        return self
+
     def matmul(self, y, transpose=False):
         """tf.matmul(M, y, adjoint_a=transpose)."""
         import torch

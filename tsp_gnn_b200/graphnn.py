@@ -230,7 +230,8 @@ class GraphNN(object):
         device = next(iter(h.values())).device
         c = {v: (dev_tensor(LSTM_initial_states[v]) if v in LSTM_initial_states else torch.zeros_like(h[v])) for v in h}
         used = {u["mat"] for ups in self.loop.values() for u in ups if "mat" in u}
-        coo = {m: generic.CooMatrix(adjacency_matrices[m], device) for m in used
+        as_coo = lambda M: M if isinstance(M, generic.CooMatrix) else generic.CooMatrix(M, device)
+        coo = {m: as_coo(adjacency_matrices[m]) for m in used
                if any("var" in u and u.get("mat") == m for ups in self.loop.values() for u in ups)}
         raw = {m: dev_tensor(adjacency_matrices[m]) for m in used
                if any("var" not in u and u.get("mat") == m for ups in self.loop.values() for u in ups)}

@@ -79,11 +79,11 @@ def build_network(d, mode="bf16x3", device=0):
             "E": [{"mat": "EV", "msg": "V_msg_E", "var": "V"}],                       # E(t+1) <- Eu(EV x V_msg_E(V(t)))
         },
         name="TSP")                                                          # model.py:57-94
-    if gnn._kernel_roles is None:
-        raise NotImplementedError(
-            "build_network(d=%r): the Session / engine path is built for the reference's default embedding size "
-            "d=64 (train.py:108); other sizes run only through GraphNN's generic CUDA path (GraphNN.__call__ "
-            "with its own parameters), not through the fused kernels behind sess.run" % (d,))
+    if int(d) != d or d < 8 or int(d / 8) < 1:
+        raise ValueError("build_network(d=%r): d must be an integer >= 8 (E_init_MLP has a layer of d/8 units, "
+                         "model.py:34)" % (d,))
+    # d == 64 (train.py:108, the reference's default) runs on the fused kernels; any other size runs the same graph
+    # op by op on the generic CUDA building blocks (inference fetches only, see _GenericRunner)
 
     E_vote_MLP = Mlp(layer_sizes=[d for _ in range(3)], activations=["relu" for _ in range(3)], output_size=1,
                      name="E_vote", name_internal_layers=True, kernel_initializer="xavier",
@@ -123,6 +123,59 @@ def _metrics(logits, predictions, route_exists):
     }
 
 
+class _GenericRunner(object):
+    """build_network(d != 64) behind ``Session.run``: model.py:33-51,118-147 executed op by op on the generic
+    CUDA building blocks of tsp_gnn_b200/generic.py (dense layer, COO matrix product, LayerNorm-LSTM cell of any
+    size) -- the reference's ``-d`` flag (train.py:108) for the inference fetches.  Every arithmetic step is a
+    libtspgnn kernel: the vertex tiling is a dense layer on a column of ones, the per-instance vote mean a COO
+    product with 1/n_edges entries, the sigmoid a 1x1 dense layer.  The reverse pass exists for d = 64 only."""
+
+    def __init__(self, GNN):
+        cfg = GNN["_config"]
+        self.d, self.device = int(cfg["d"]), cfg["device"]
+        self.gnn, self.e_init, self.e_vote = GNN["gnn"], cfg["E_init_MLP"], cfg["E_vote_MLP"]
+        self._vinit = None
+        self._plan = None
+        self.states = None
+
+    def set_params(self, params):
+        import torch
+        self.e_init.set_parameters(params)
+        self.e_vote.set_parameters(params)
+        self.gnn.set_parameters(params)
+        dev = torch.device("cuda", self.device)
+        v = np.asarray(params["V_init"], dtype=np.float32).reshape(1, self.d) / np.float32(np.sqrt(np.float32(self.d)))
+        self._vinit = torch.from_numpy(np.ascontiguousarray(v)).to(dev)          # model.py:46-51
+        self._one = torch.ones(1, 1, dtype=torch.float32, device=dev)
+
+    def plan(self, nv, ne, src, dst):
+        import torch
+        from . import generic
+        dev = torch.device("cuda", self.device)
+        nE, nV, B = int(ne.sum()), int(nv.sum()), int(ne.shape[0])
+        e = np.arange(nE, dtype=np.int32)
+        EV = generic.CooMatrix.from_entries(np.concatenate([e, e]), np.concatenate([src, dst]), None, (nE, nV), dev)
+        inst_of_edge = np.repeat(np.arange(B, dtype=np.int32), ne)
+        mean = generic.CooMatrix.from_entries(inst_of_edge, e, (1.0 / ne.astype(np.float64))[inst_of_edge], (B, nE), dev)
+        self._plan = (EV, mean, torch.ones(nV, 1, dtype=torch.float32, device=dev), nE, nV, B)
+
+    def forward(self, W, C, time_steps):
+        import torch
+        from . import generic
+        EV, mean, ones_v, nE, nV, B = self._plan
+        dev = ones_v.device
+        with torch.cuda.device(dev):
+            wc = torch.from_numpy(np.ascontiguousarray(np.stack([W, C], axis=1), dtype=np.float32)).to(dev)
+            Eh = self.e_init(wc)                                              # model.py:33-43
+            Vh = generic.dense(ones_v, self._vinit)                           # model.py:46-51: tile(V_init / sqrt(d))
+            st = self.gnn._call_generic({"EV": EV}, {"V": Vh, "E": Eh}, time_steps, {})
+            votes = self.e_vote(st["E"].h)                                    # model.py:124-128
+            logits = mean.matmul(votes)                                       # model.py:134-145
+            preds = generic.dense(logits, self._one, None, "sigmoid")         # model.py:147
+            self.states = st
+            return logits.reshape(-1).cpu().numpy(), preds.reshape(-1).cpu().numpy()
+
+
 class Session(object):
     """tf.Session stand-in bound to one GPU engine."""
 
@@ -132,6 +185,9 @@ class Session(object):
         self._params = None
         self._params_stale = False      # the device holds newer variables than self._params
         self._plan_key = None
+        self._generic = None            # _GenericRunner when the network is not the fused kernels' d = 64
+        if GNN is not None and GNN["gnn"]._kernel_roles is None:
+            self._generic = _GenericRunner(GNN)
 
     def __enter__(self):
         return self
@@ -158,7 +214,10 @@ class Session(object):
     def set_variables(self, params):
         self._params = {k: np.asarray(v, dtype=np.float32) for k, v in params.items()}
         self._params_stale = False
-        self._ensure_engine().set_params(self._params)
+        if self._generic is not None:
+            self._generic.set_params(self._params)
+        else:
+            self._ensure_engine().set_params(self._params)
 
     def get_variables(self):
         if self._params_stale:
@@ -168,6 +227,8 @@ class Session(object):
 
     def get_optimizer_state(self):
         """Adam slots + step (tf.train.Saver stores them with the variables, util.py:35)."""
+        if self._generic is not None:
+            return None
         return self._ensure_engine().get_optimizer_state()
 
     def set_optimizer_state(self, state):
@@ -179,12 +240,12 @@ class Session(object):
         ckpt = _params.load_checkpoint(path)
         self.set_variables(_params.load_weights(path))
         opt = _params.named_to_optimizer_state(ckpt, self._gnn["_config"]["d"])
-        if opt is not None:
+        if opt is not None and self._generic is None:
             self.set_optimizer_state(opt)
 
     def save_weights(self, path):
         """util.save_weights: variables + Adam slots + beta powers (tf.train.Saver() default var_list)."""
-        opt = self.get_optimizer_state() if self._engine is not None else None
+        opt = self.get_optimizer_state() if (self._engine is not None and self._generic is None) else None
         _params.save_weights(self.get_variables(), path, optimizer_state=opt)
 
     # -- run ------------------------------------------------------------------------
@@ -207,7 +268,12 @@ class Session(object):
         for need in ("EV", "edge_weight", "target_cost", "time_steps", "n_vertices", "edges"):
             if need not in feed:
                 raise ValueError("You must feed a value for placeholder %r" % need)
-        eng = self._ensure_engine()
+        if train and self._generic is not None:
+            raise NotImplementedError(
+                "train_step at d=%d: the reverse pass is built for the reference's default embedding size d=64 "
+                "(train.py:108); other sizes run the inference fetches on the generic CUDA path"
+                % self._gnn["_config"]["d"])
+        eng = self._generic if self._generic is not None else self._ensure_engine()
         EV = feed["EV"]
         if not isinstance(EV, Incidence):
             from .engine import dense_ev_to_coo
@@ -232,6 +298,8 @@ class Session(object):
                 raise ValueError("You must feed a value for placeholder 'route_exists'")
             _, logits, preds = eng.train_step_host(W, C, feed["route_exists"], int(feed["time_steps"]))
             self._params_stale = True
+        elif self._generic is not None:
+            logits, preds = eng.forward(W, C, int(feed["time_steps"]))
         else:
             logits, preds = eng.forward_host(W, C, int(feed["time_steps"]))
         out = {"predictions": preds, "logits": logits, "train_step": None}
@@ -239,7 +307,10 @@ class Session(object):
             if "route_exists" not in feed:
                 raise ValueError("You must feed a value for placeholder 'route_exists'")
             out.update(_metrics(logits, preds, feed["route_exists"]))
-        if "last_states" in names:
+        if "last_states" in names and self._generic is not None:
+            out["last_states"] = {v: LSTMStateTuple(c=t.c.cpu().numpy(), h=t.h.cpu().numpy())
+                                  for v, t in eng.states.items()}
+        elif "last_states" in names:
             st = eng.get_states()
             out["last_states"] = {v: LSTMStateTuple(c=st[v][0].cpu().numpy(), h=st[v][1].cpu().numpy())
                                   for v in ("V", "E")}
