@@ -10,13 +10,13 @@
 // product, fp32 accumulation in TMEM), so the reverse pass sees the same ~2^-16 relative operand error as
 // the forward pass whose state it differentiates.
 //
-// Structure (one persistent CTA per SM, 384 threads, tiles of 128 rows):
+// Structure (one persistent CTA per SM, 512 threads, tiles of 128 rows):
 //   warps 0-3, 4-7 : two epilogue warpgroups, one tile each.  The accumulator is read in the 16-lane
 //                    "quad" TMEM shape, so the four threads of a quad hold 32 contiguous bytes of a row and
 //                    the fp32 row-major output goes to global memory in full sectors without a shared-memory
 //                    transposition (8 rows x 32 bytes per warp instruction).
 //   warp  8        : tcgen05.mma issuer, owns the TMEM allocation (two accumulators of 64 NB columns)
-//   warps 9-11     : producers: 128 rows x 64 columns of X per k-block, fp32 -> bf16 hi / lo planes in the
+//   warps 9-15     : producers: 128 rows x 64 columns of X per k-block, fp32 -> bf16 hi / lo planes in the
 //                    un-swizzled K-major canonical layout (chunk-major, as the forward kernels' tile images),
 //                    through a ring of 32 KB slots
 // The B operand (both bf16 planes of Wm, up to 128 KB) is built once per CTA from the fp32 parameters.
@@ -45,8 +45,14 @@ struct TRSmem {
   static_assert(DYN_BYTES <= 232448, "row GEMM: shared memory budget (227 KB)");
 };
 
+// 512 threads: the producers are bound by the latency of their loads (Little: 6 TB/s x ~1 us = 40 KB in flight per
+// SM), so seven producer warps keep a whole 32 KB k-block of a tile in flight (three warps with eight loads per lane
+// held 12 KB: 1.3-2 TB/s).  Registers: 8 x 152 (epilogue) + 8 x 104 (issuer, producers) per lane = the whole file.
+constexpr int TR_THREADS = 512;
+constexpr int TR_PRODUCERS = 7;
+
 template <int KB, int NB, bool TRANS, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemmArgs a) {
+__global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemmArgs a) {
   using L = TRSmem<KB, NB>;
   constexpr int N = 64 * NB;
   extern __shared__ uint8_t smem_raw[];
@@ -67,7 +73,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
 
   if (tid == 0) {
     for (int s = 0; s < L::NSLOT; ++s) {
-      ptx::mbar_init(&full[s], NUM_GATHER_WARPS);
+      ptx::mbar_init(&full[s], TR_PRODUCERS);
       ptx::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
   if (warp == 8) ptx::tmem_alloc(tmem_slot, 512);
   // ---- B operand: Wm[k, n] (TRANS: Ws[n, k], else Ws[k, n]; zero outside w_rows x w_cols), bf16 hi / lo images.
   // One 16-byte chunk = 8 consecutive k of one output feature n; consecutive threads take consecutive n.
-  for (int i = tid; i < KB * 8 * N; i += TC_THREADS) {
+  for (int i = tid; i < KB * 8 * N; i += TR_THREADS) {
     const int n = i % N, kc = i / N;              // kc: chunk of 8 k-values, 0 .. 8 KB - 1
     float v[8];
 #pragma unroll
@@ -107,6 +113,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 8) {
+    ptx::setmaxnreg_inc<152>();
     // ---- epilogue: accumulator -> (+bias, ReLU / mask / accumulate) -> row-major fp32 Y -----------------
     const int e = warp >> 2, q4 = warp & 3;
     const int tq0 = lane & 3, tq1 = lane >> 2;
@@ -180,6 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
       }
     }
   } else if (warp == 8) {
+    ptx::setmaxnreg_dec<104>();
     // ---- MMA issuer ----------------------------------------------------------------------------------
     constexpr uint32_t IDESC = ptx::umma_idesc_bf16(128, N);
     const uint64_t adesc0 = ptx::umma_desc_k_nosw(ptx::smem_u32(ring), 2048, 128);
@@ -212,8 +220,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
     }
   } else {
     // ---- producers: X block -> bf16 hi / lo operand planes ------------------------------------------------
+    ptx::setmaxnreg_dec<104>();
     const int gw = warp - 9;
     const int r8 = lane & 7, cq = lane >> 3;
+    constexpr int GPW = (16 + TR_PRODUCERS - 1) / TR_PRODUCERS;     // 8-row groups per warp (3; 16 groups in a tile)
     for (int n = 0; n < ntiles; ++n) {
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
 #pragma unroll 1
@@ -222,38 +232,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         const float* xp = a.x[kb];
         const int xld = a.xld[kb];
         const uint32_t slot_s = ptx::smem_u32(ring + slot * L::SLOT_BYTES);
-        if (suse >= 1) ptx::mbar_wait(&empty[slot], (suse - 1) & 1);
+        // every load of this warp's share of the block first (up to twelve 16-byte loads per lane), then the slot
+        // wait: the loads do not touch the slot
+        float4 u[GPW][2][2];
 #pragma unroll
-        for (int gb = 0; gb < 6; gb += 2) {             // two 8-row groups = eight 16-byte loads in flight per lane
-          float4 u[2][2][2];
+        for (int i = 0; i < GPW; ++i) {
+          const int g = gw + TR_PRODUCERS * i;
+          const int64_t row = row0 + g * 8 + r8;
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            const int g = gw + NUM_GATHER_WARPS * (gb + g2);
-            const int64_t row = row0 + g * 8 + r8;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              u[g2][j][0] = u[g2][j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (g < 16 && row < a.n_rows) {
-                const float4* p = reinterpret_cast<const float4*>(xp + row * xld + (cq + 4 * j) * 8);
-                u[g2][j][0] = p[0];
-                u[g2][j][1] = p[1];
-              }
+          for (int j = 0; j < 2; ++j) {
+            u[i][j][0] = u[i][j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g < 16 && row < a.n_rows) {
+              const float4* p = reinterpret_cast<const float4*>(xp + row * xld + (cq + 4 * j) * 8);
+              u[i][j][0] = p[0];
+              u[i][j][1] = p[1];
             }
           }
+        }
+        if (suse >= 1) ptx::mbar_wait(&empty[slot], (suse - 1) & 1);
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            const int g = gw + NUM_GATHER_WARPS * (gb + g2);
-            if (g < 16) {
+        for (int i = 0; i < GPW; ++i) {
+          const int g = gw + TR_PRODUCERS * i;
+          if (g < 16) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const float x[8] = {u[g2][j][0].x, u[g2][j][0].y, u[g2][j][0].z, u[g2][j][0].w,
-                                    u[g2][j][1].x, u[g2][j][1].y, u[g2][j][1].z, u[g2][j][1].w};
-                uint4 hi, lo;
-                split8(x, hi, lo);
-                const uint32_t off = slot_s + (cq + 4 * j) * 2048 + (g * 8 + r8) * 16;
-                ptx::sts128(off, hi);
-                ptx::sts128(off + PLANE_BYTES, lo);
-              }
+            for (int j = 0; j < 2; ++j) {
+              const float x[8] = {u[i][j][0].x, u[i][j][0].y, u[i][j][0].z, u[i][j][0].w,
+                                  u[i][j][1].x, u[i][j][1].y, u[i][j][1].z, u[i][j][1].w};
+              uint4 hi, lo;
+              split8(x, hi, lo);
+              const uint32_t off = slot_s + (cq + 4 * j) * 2048 + (g * 8 + r8) * 16;
+              ptx::sts128(off, hi);
+              ptx::sts128(off + PLANE_BYTES, lo);
             }
           }
         }

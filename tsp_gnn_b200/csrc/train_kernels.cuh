@@ -351,86 +351,188 @@ __device__ __forceinline__ void ln_bwd2(const float (&dy)[2], const float (&uh)[
   du[1] = r * (a1 - m1 - uh[1] * m2);
 }
 
-__global__ void __launch_bounds__(256, 3) lstm_bwd_kernel(float* __restrict__ z, const float* __restrict__ c_prev,
+// Half-warp sums (lanes 0-15 and 16-31 each reduce their own values), NS independent scalars at once so that the
+// shuffle chains of several reductions overlap.
+template <int NS>
+__device__ __forceinline__ void hw_sum(float (&v)[NS]) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < NS; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+}
+
+// reverse of y = uh * gamma + beta for a 64-vector held as 4 values per lane of a half-warp
+__device__ __forceinline__ void ln_bwd4(const float (&dy)[4], const float (&uh)[4], float r, const float (&gamma)[4],
+                                        float (&du)[4], float (&dgam)[4], float (&dbet)[4]) {
+  float a[4], m[2] = {0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    dgam[q] += dy[q] * uh[q];
+    dbet[q] += dy[q];
+    a[q] = dy[q] * gamma[q];
+    m[0] += a[q];
+    m[1] = fmaf(a[q], uh[q], m[1]);
+  }
+  hw_sum<2>(m);
+  const float m1 = m[0] * (1.0f / 64.0f), m2 = m[1] * (1.0f / 64.0f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) du[q] = r * (a[q] - m1 - uh[q] * m2);
+}
+
+// One HALF-WARP per row: lane hl = lane & 15 holds columns 4 hl .. 4 hl + 3 of every 64-vector of the row, so every
+// access is a 16-byte load / store (a row of z is four of them per lane), a reduction takes four shuffle steps that
+// serve two rows at once (40 shuffles per row instead of 100 with a warp per row and 4-byte accesses), and the four
+// gate LayerNorms reduce together.  z is overwritten with dz, g_c with dL/dc.
+__global__ void __launch_bounds__(256, 2) lstm_bwd_kernel(float* __restrict__ z, const float* __restrict__ c_prev,
                                                        const float* __restrict__ g_h, float* __restrict__ g_c,
                                                        int64_t n_rows, const float* __restrict__ params,
                                                        float* __restrict__ grads, const LnOffsets off) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  float gam[5][2], bet[5][2], dgam[5][2], dbet[5][2];
+  const int lane = threadIdx.x & 31, hl = lane & 15;
+  const int64_t hw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
+  const int64_t n_hw = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 4;
+  // LayerNorm parameters: shared memory (read per row as 16-byte pieces), the 40 gradient sums stay in registers
+  __shared__ __align__(16) float prm[2 * 5 * 64];
+  __shared__ float red[2 * 5 * 64];
+  for (int i = threadIdx.x; i < 2 * 5 * 64; i += blockDim.x) {
+    const int g = (i % 320) >> 6, col = i & 63;
+    prm[i] = params[(i < 320 ? off.gamma[g] : off.beta[g]) + col];
+    red[i] = 0.f;
+  }
+  __syncthreads();
+  float dgam[5][4], dbet[5][4];
 #pragma unroll
   for (int g = 0; g < 5; ++g)
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      gam[g][q] = params[off.gamma[g] + lane + 32 * q];
-      bet[g][q] = params[off.beta[g] + lane + 32 * q];
+    for (int q = 0; q < 4; ++q) {
       dgam[g][q] = 0.f;
       dbet[g][q] = 0.f;
     }
-  for (int64_t row = warp; row < n_rows; row += n_warps) {
-    float zg[4][2], uh[4][2], r[4], c[2], gh[2], gc[2];
+  auto ld4 = [&](const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * hl);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  };
+  // both halves of a warp run the same number of iterations (the shuffles are warp-wide): rows past the end are
+  // computed on zeros and never stored
+  const int64_t n_iter = (n_rows + n_hw - 1) / n_hw;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t row = hw + it * n_hw;
+    const bool live = row < n_rows;
+    float zg[4][4], uh[4][4], r[4], c[4], gh[4], gc[4];
+    {
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t[7];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      zg[g][0] = z[row * 256 + g * 64 + lane];
-      zg[g][1] = z[row * 256 + g * 64 + lane + 32];
+      for (int g = 0; g < 4; ++g) t[g] = live ? *reinterpret_cast<const float4*>(z + row * 256 + g * 64 + 4 * hl) : zero;
+      t[4] = live ? *reinterpret_cast<const float4*>(c_prev + row * 64 + 4 * hl) : zero;
+      t[5] = live ? *reinterpret_cast<const float4*>(g_h + row * 64 + 4 * hl) : zero;
+      t[6] = live ? *reinterpret_cast<const float4*>(g_c + row * 64 + 4 * hl) : zero;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        zg[g][0] = t[g].x; zg[g][1] = t[g].y; zg[g][2] = t[g].z; zg[g][3] = t[g].w;
+      }
+      c[0] = t[4].x; c[1] = t[4].y; c[2] = t[4].z; c[3] = t[4].w;
+      gh[0] = t[5].x; gh[1] = t[5].y; gh[2] = t[5].z; gh[3] = t[5].w;
+      gc[0] = t[6].x; gc[1] = t[6].y; gc[2] = t[6].z; gc[3] = t[6].w;
     }
+    // forward LayerNorm statistics of the four gates, reduced together
+    {
+      float m[4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      c[q] = c_prev[row * 64 + lane + 32 * q];
-      gh[q] = g_h[row * 64 + lane + 32 * q];
-      gc[q] = g_c[row * 64 + lane + 32 * q];
+      for (int g = 0; g < 4; ++g) m[g] = (zg[g][0] + zg[g][1]) + (zg[g][2] + zg[g][3]);
+      hw_sum<4>(m);
+      float v[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float mean = m[g] * (1.0f / 64.0f);
+        v[g] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uh[g][q] = zg[g][q] - mean;
+          v[g] = fmaf(uh[g][q], uh[g][q], v[g]);
+        }
+      }
+      hw_sum<4>(v);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        r[g] = rsqrtf(v[g] * (1.0f / 64.0f) + LN_EPS);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) uh[g][q] *= r[g];
+      }
     }
+    float si[4], sf[4], so[4], jj[4], gg[4], ct[4];
+    {
+      float gm[4][4], bt[4][4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) ln_fwd2(zg[g], uh[g], r[g]);
-    float si[2], sf[2], so[2], jj[2], gg[2], ct[2];
+      for (int g = 0; g < 4; ++g) {
+        ld4(prm + g * 64, gm[g]);
+        ld4(prm + 320 + g * 64, bt[g]);
+      }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      si[q] = sigmoidf_acc(uh[0][q] * gam[0][q] + bet[0][q]);
-      jj[q] = uh[1][q] * gam[1][q] + bet[1][q];
-      gg[q] = fmaxf(jj[q], 0.f);
-      sf[q] = sigmoidf_acc(uh[2][q] * gam[2][q] + bet[2][q] + FORGET_BIAS);
-      so[q] = sigmoidf_acc(uh[3][q] * gam[3][q] + bet[3][q]);
-      ct[q] = c[q] * sf[q] + si[q] * gg[q];
+      for (int q = 0; q < 4; ++q) {
+        si[q] = sigmoidf_acc(uh[0][q] * gm[0][q] + bt[0][q]);
+        jj[q] = uh[1][q] * gm[1][q] + bt[1][q];
+        gg[q] = fmaxf(jj[q], 0.f);
+        sf[q] = sigmoidf_acc(uh[2][q] * gm[2][q] + bt[2][q] + FORGET_BIAS);
+        so[q] = sigmoidf_acc(uh[3][q] * gm[3][q] + bt[3][q]);
+        ct[q] = c[q] * sf[q] + si[q] * gg[q];
+      }
     }
-    float ch[2], cr;
-    ln_fwd2(ct, ch, cr);
-    float d_so[2], d_cn[2], d_ct[2];
+    float ch[4], cr;
+    {
+      float m[1] = {(ct[0] + ct[1]) + (ct[2] + ct[3])};
+      hw_sum<1>(m);
+      const float mean = m[0] * (1.0f / 64.0f);
+      float v[1] = {0.f};
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float cn = ch[q] * gam[4][q] + bet[4][q];
-      d_so[q] = gh[q] * fmaxf(cn, 0.f);
-      d_cn[q] = gc[q] + ((cn > 0.f) ? gh[q] * so[q] : 0.f);
+      for (int q = 0; q < 4; ++q) {
+        ch[q] = ct[q] - mean;
+        v[0] = fmaf(ch[q], ch[q], v[0]);
+      }
+      hw_sum<1>(v);
+      cr = rsqrtf(v[0] * (1.0f / 64.0f) + LN_EPS);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ch[q] *= cr;
     }
-    ln_bwd2(d_cn, ch, cr, gam[4], d_ct, dgam[4], dbet[4]);
-    float dgate[4][2];
+    float d_so[4], d_cn[4], d_ct[4], gmv[4];
+    {
+      float bt[4];
+      ld4(prm + 4 * 64, gmv);
+      ld4(prm + 320 + 4 * 64, bt);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      g_c[row * 64 + lane + 32 * q] = d_ct[q] * sf[q];
+      for (int q = 0; q < 4; ++q) {
+        const float cn = ch[q] * gmv[q] + bt[q];
+        d_so[q] = gh[q] * fmaxf(cn, 0.f);
+        d_cn[q] = gc[q] + ((cn > 0.f) ? gh[q] * so[q] : 0.f);
+      }
+    }
+    ln_bwd4(d_cn, ch, cr, gmv, d_ct, dgam[4], dbet[4]);
+    float dgate[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
       dgate[0][q] = d_ct[q] * gg[q] * si[q] * (1.0f - si[q]);
       dgate[1][q] = (jj[q] > 0.f) ? d_ct[q] * si[q] : 0.f;
       dgate[2][q] = d_ct[q] * c[q] * sf[q] * (1.0f - sf[q]);
       dgate[3][q] = d_so[q] * so[q] * (1.0f - so[q]);
     }
+    if (live)
+      *reinterpret_cast<float4*>(g_c + row * 64 + 4 * hl) =
+          make_float4(d_ct[0] * sf[0], d_ct[1] * sf[1], d_ct[2] * sf[2], d_ct[3] * sf[3]);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      float du[2];
-      ln_bwd2(dgate[g], uh[g], r[g], gam[g], du, dgam[g], dbet[g]);
-      z[row * 256 + g * 64 + lane] = du[0];
-      z[row * 256 + g * 64 + lane + 32] = du[1];
+      float du[4];
+      ld4(prm + g * 64, gmv);
+      ln_bwd4(dgate[g], uh[g], r[g], gmv, du, dgam[g], dbet[g]);
+      if (live) *reinterpret_cast<float4*>(z + row * 256 + g * 64 + 4 * hl) = make_float4(du[0], du[1], du[2], du[3]);
     }
   }
-  // LayerNorm parameter gradients: summed over the CTA's warps in shared memory, then one global
+  // LayerNorm parameter gradients: summed over the CTA's half-warps in shared memory, then one global
   // atomic per parameter and CTA (640 addresses would otherwise serialise every warp of the grid)
-  __shared__ float red[2 * 5 * 64];
-  for (int i = threadIdx.x; i < 2 * 5 * 64; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
 #pragma unroll
   for (int g = 0; g < 5; ++g)
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      atomicAdd(red + g * 64 + lane + 32 * q, dgam[g][q]);
-      atomicAdd(red + 320 + g * 64 + lane + 32 * q, dbet[g][q]);
+    for (int q = 0; q < 4; ++q) {
+      atomicAdd(red + g * 64 + 4 * hl + q, dgam[g][q]);
+      atomicAdd(red + 320 + g * 64 + 4 * hl + q, dbet[g][q]);
     }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * 5 * 64; i += blockDim.x) {
