@@ -142,10 +142,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
       ptx::mbar_wait(&acc_full[e], use & 1);
       ptx::tcgen05_fence_after();
 #pragma unroll 1
-      for (int nb = 0; nb < NB; ++nb) {
+      for (int nbi = 0; nbi < NB; ++nbi) {
+        // CTAs start at different 64-column blocks: with every CTA on block 0, then 1, ... all accesses of the machine
+        // fall into the same quarter of the 1 KB rows of a 256-wide matrix at any one time
+        const int nb = (nbi + static_cast<int>(blockIdx.x)) % NB;
         float qa[32], qb[32];     // rows tq1, tq1 + 8 (qa) and tq1 + 16, tq1 + 24 (qb); reg[4k + 2hi + j] = column 8k + 2 tq0 + j
         ptx::tmem_ld_quad64(t_acc + nb * 64, qa, qb);
-        if (nb == NB - 1) {       // last TMEM read of this tile: hand the accumulator back
+        if (nbi == NB - 1) {      // last TMEM read of this tile: hand the accumulator back
           ptx::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&acc_empty[e]);
@@ -197,8 +200,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
       if (k_use >= 1) ptx::mbar_wait(&acc_empty[acc], (k_use - 1) & 1);
       const uint32_t d_tmem = tmem + acc * 256;
 #pragma unroll 1
-      for (int kb = 0; kb < KB; ++kb) {
-        const int seq = n * KB + kb, slot = seq % L::NSLOT, suse = seq / L::NSLOT;
+      for (int kbi = 0; kbi < KB; ++kbi) {
+        const int kb = (kbi + static_cast<int>(blockIdx.x)) % KB;      // the producers' order (see there)
+        const int seq = n * KB + kbi, slot = seq % L::NSLOT, suse = seq / L::NSLOT;
         ptx::mbar_wait(&full[slot], suse & 1);
         ptx::tcgen05_fence_after();
         if (ptx::elect_one()) {
@@ -210,10 +214,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
             for (int k = 0; k < 4; ++k)
               ptx::umma_bf16_ss(d_tmem, aslot + ((pa_[cb] * PLANE_BYTES + k * 4096) >> 4),
                                 bdesc0 + static_cast<uint32_t>(((pb_[cb] * KB + kb) * (N * 128) + k * (2 * N * 16)) >> 4), IDESC,
-                                (kb | cb | k) ? 1u : 0u);
+                                (kbi | cb | k) ? 1u : 0u);
           }
           ptx::umma_commit(&empty[slot]);
-          if (kb == KB - 1) ptx::umma_commit(&acc_full[acc]);
+          if (kbi == KB - 1) ptx::umma_commit(&acc_full[acc]);
         }
         __syncwarp();
       }
@@ -227,26 +231,24 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
     for (int n = 0; n < ntiles; ++n) {
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
 #pragma unroll 1
-      for (int kb = 0; kb < KB; ++kb) {
-        const int seq = n * KB + kb, slot = seq % L::NSLOT, suse = seq / L::NSLOT;
+      for (int kbi = 0; kbi < KB; ++kbi) {
+        const int kb = (kbi + static_cast<int>(blockIdx.x)) % KB;      // CTAs start at different k-blocks (see the epilogue)
+        const int seq = n * KB + kbi, slot = seq % L::NSLOT, suse = seq / L::NSLOT;
         const float* xp = a.x[kb];
         const int xld = a.xld[kb];
         const uint32_t slot_s = ptx::smem_u32(ring + slot * L::SLOT_BYTES);
         // every load of this warp's share of the block first (up to twelve 16-byte loads per lane), then the slot
         // wait: the loads do not touch the slot
-        float4 u[GPW][2][2];
+        float u[GPW][2][8];                             // one 32-byte load (LDG.256) per lane and chunk
 #pragma unroll
         for (int i = 0; i < GPW; ++i) {
           const int g = gw + TR_PRODUCERS * i;
           const int64_t row = row0 + g * 8 + r8;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            u[i][j][0] = u[i][j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < 16 && row < a.n_rows) {
-              const float4* p = reinterpret_cast<const float4*>(xp + row * xld + (cq + 4 * j) * 8);
-              u[i][j][0] = p[0];
-              u[i][j][1] = p[1];
-            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) u[i][j][e] = 0.f;
+            if (g < 16 && row < a.n_rows) ptx::ldg256_coherent(xp + row * xld + (cq + 4 * j) * 8, u[i][j]);
           }
         }
         if (suse >= 1) ptx::mbar_wait(&empty[slot], (suse - 1) & 1);
@@ -256,10 +258,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
           if (g < 16) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const float x[8] = {u[i][j][0].x, u[i][j][0].y, u[i][j][0].z, u[i][j][0].w,
-                                  u[i][j][1].x, u[i][j][1].y, u[i][j][1].z, u[i][j][1].w};
               uint4 hi, lo;
-              split8(x, hi, lo);
+              split8(u[i][j], hi, lo);
               const uint32_t off = slot_s + (cq + 4 * j) * 2048 + (g * 8 + r8) * 16;
               ptx::sts128(off, hi);
               ptx::sts128(off + PLANE_BYTES, lo);
@@ -384,45 +384,42 @@ __global__ void __launch_bounds__(XT2_THREADS, 1) tc_xtdy_kernel(const Xtdy2Args
       const int st = n & 1, use = n >> 1;
       const int64_t row0 = static_cast<int64_t>(t0 + n) * SROWS;
       const uint32_t xs = ptx::smem_u32(smem + st * L::STAGE), ys = xs + 2 * L::XP;
-      if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
-#pragma unroll 1
-      for (int tb = warp; tb < ntask; tb += 64) {       // eight tasks (sixteen 16-byte loads) in flight per lane
-        float4 u[8][2];
-        uint32_t dst[8];
+      // every load of the stage first (up to twelve tasks = twenty-four 16-byte loads per lane: the producers are bound
+      // by the latency of their loads, two batches per stage made a stage two round trips), then the stage wait
+      constexpr int TPW = 12;                           // tasks per warp: <64,32> with two k-blocks has 96, <128,8> 64 or 96
+      float u[TPW][8];                                  // one 32-byte load (LDG.256) per task and lane
+      uint32_t dst[TPW];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int task = tb + 8 * i;
-          u[i][0] = u[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          dst[i] = 0u;
-          if (task < ntask) {
-            const int g = task / quads, qd = task % quads;
-            const int64_t row = row0 + g * 8 + r8;
-            const float* p;
-            if (qd < 2 * KB) {
-              const int kb = qd >> 1, chunk = (qd & 1) * 4 + cq;           // chunk inside the 64-column block
-              p = (kb == 0 ? a.x[0] : a.x[1]) + row * (kb == 0 ? a.xld[0] : a.xld[1]) + chunk * 8;
-              dst[i] = xs + (kb * 8 + chunk) * L::CS + (g * 8 + r8) * 16;
-            } else {
-              const int chunk = (qd - 2 * KB) * 4 + cq;
-              p = dyp + row * a.dyld + chunk * 8;
-              dst[i] = ys + chunk * L::CS + (g * 8 + r8) * 16;
-            }
-            if (row < a.n_rows) {
-              u[i][0] = reinterpret_cast<const float4*>(p)[0];
-              u[i][1] = reinterpret_cast<const float4*>(p)[1];
-            }
+      for (int i = 0; i < TPW; ++i) {
+        const int task = warp + 8 * i;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[i][e] = 0.f;
+        dst[i] = 0u;
+        if (task < ntask) {
+          const int g = task / quads, qd = task % quads;
+          const int64_t row = row0 + g * 8 + r8;
+          const float* p;
+          if (qd < 2 * KB) {
+            const int kb = qd >> 1, chunk = (qd & 1) * 4 + cq;           // chunk inside the 64-column block
+            p = (kb == 0 ? a.x[0] : a.x[1]) + row * (kb == 0 ? a.xld[0] : a.xld[1]) + chunk * 8;
+            dst[i] = xs + (kb * 8 + chunk) * L::CS + (g * 8 + r8) * 16;
+          } else {
+            const int chunk = (qd - 2 * KB) * 4 + cq;
+            p = dyp + row * a.dyld + chunk * 8;
+            dst[i] = ys + chunk * L::CS + (g * 8 + r8) * 16;
           }
+          if (row < a.n_rows) ptx::ldg256_coherent(p, u[i]);
         }
+      }
+      if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (tb + 8 * i < ntask) {
-            const float x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const bool is_x = dst[i] < ys;
-            ptx::sts128(dst[i], hi);
-            ptx::sts128(dst[i] + (is_x ? L::XP : L::YP), lo);
-          }
+      for (int i = 0; i < TPW; ++i) {
+        if (warp + 8 * i < ntask) {
+          uint4 hi, lo;
+          split8(u[i], hi, lo);
+          const bool is_x = dst[i] < ys;
+          ptx::sts128(dst[i], hi);
+          ptx::sts128(dst[i] + (is_x ? L::XP : L::YP), lo);
         }
       }
       if (ones && warp < SROWS / 32) {
@@ -705,7 +702,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
       const uint32_t ds = ptx::smem_u32(smem + L::STAGE_OFF + st * L::STAGE), as = ds + 2 * L::DP;
       // the tile's sixteen 16-byte loads per lane are requested before the stage is waited for
-      float4 u[8][2];
+      float u[8][8];                                    // one 32-byte load (LDG.256) per task and lane
       uint32_t dst[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -715,19 +712,16 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
         const int chunk = (qd & 1) * 4 + cq;
         const float* p = (qd < 2) ? a.d + row * a.dld + chunk * 8 : a.a + row * a.ald + chunk * 8;
         dst[i] = ((qd < 2) ? ds : as) + chunk * 2048 + (g * 8 + r8) * 16;
-        u[i][0] = u[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < a.n_rows) {
-          u[i][0] = reinterpret_cast<const float4*>(p)[0];
-          u[i][1] = reinterpret_cast<const float4*>(p)[1];
-        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[i][e] = 0.f;
+        if (row < a.n_rows) ptx::ldg256_coherent(p, u[i]);
       }
       static_assert(ntask == 64, "eight producer warps, eight tasks each");
       if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float x[8] = {u[i][0].x, u[i][0].y, u[i][0].z, u[i][0].w, u[i][1].x, u[i][1].y, u[i][1].z, u[i][1].w};
         uint4 hi, lo;
-        split8(x, hi, lo);
+        split8(u[i], hi, lo);
         const bool is_d = dst[i] < as;
         ptx::sts128(dst[i], hi);
         ptx::sts128(dst[i] + (is_d ? L::DP : L::AP), lo);
