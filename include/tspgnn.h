@@ -48,7 +48,8 @@ int tspgnn_version(void);
 int64_t tspgnn_param_count(int d);
 
 /* Replaces build_network(d) graph construction + tf.Session() (model.py:9, train.py:202-206).
- * Only d == 64 (the reference default, train.py:108) is implemented.  */
+ * Only d == 64 (the reference default, train.py:108) is implemented here; the Python mirror serves other sizes
+ * through the generic building blocks at the end of this header (tsp_gnn_b200/model.py, inference only).  */
 int tspgnn_create(int d, int mode, int device, tspgnn_handle* out);
 int tspgnn_destroy(tspgnn_handle h);
 int tspgnn_get_mode(tspgnn_handle h);
