@@ -456,6 +456,30 @@ def run_ours(args):
                  "what": "tspgnn_train_step_host: H2D, training forward (32 timesteps, snapshots), reverse pass, "
                          "L2 + clip + Adam, operand refresh, D2H (model.py:157-167); per-GPU shard, no gradient "
                          "all-reduce in this leg"}
+        if world > 1:
+            # data-parallel step of the ONE global batch: every rank differentiates its shard with the global batch
+            # size as the divisor of the loss mean, ONE all-reduce of the flat gradient blob (115,529 floats) on the
+            # engine's stream, then clip + Adam identically on every rank (sharding.train_step_sharded)
+            from tsp_gnn_b200 import sharding
+            B_glob = int(shard["B"])
+            with torch.cuda.stream(eng.stream()):
+                run.dW.copy_(run.hW, non_blocking=True)
+                run.dC.copy_(run.hC, non_blocking=True)
+                dy = torch.from_numpy(np.ascontiguousarray(yf, dtype=np.float32)).to(dev)
+            eng.stream().synchronize()
+            sharding.train_step_sharded(eng, run.dW, run.dC, dy, T_STEPS, B_glob)      # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.train_steps):
+                ddp_loss, ddp_norm = sharding.train_step_sharded(eng, run.dW, run.dC, dy, T_STEPS, B_glob)
+            barrier()
+            dd_s = (time.perf_counter() - t0) / args.train_steps
+            train["data_parallel"] = {
+                "ms_per_step": 1e3 * dd_s, "instances_per_s": B_glob / dd_s, "loss": ddp_loss, "global_norm": ddp_norm,
+                "gradient_allreduce_bytes": 4 * eng.param_count,
+                "what": "train_forward + backward on this rank's shard of the global batch of %d, all-reduce of the "
+                        "gradient blob (NCCL, engine's stream), apply_gradients; device-resident inputs, wall clock "
+                        "between barriers" % B_glob}
         eng.set_params(params)                           # the legs below use the seeded variables again
 
     # ---------------- CPU baselines beside it (rank 0, N=1) ---------------------------------
