@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
     const int tq0 = lane & 3, tq1 = lane >> 2;
     const uint32_t t_acc = tmem + (static_cast<uint32_t>(q4 * 32) << 16) + e * 256;
     int use = 0;
+    long long* tl = (q4 == 0 && lane == 0) ? a.timeline : nullptr;
     for (int n = e; n < ntiles; n += 2, ++use) {
+      tl_mark(tl, e, n, 0);
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS + q4 * 32 + tq1;   // + 8 m
       // ReLU mask / previous output of a 64-wide layer: requested before the accumulator is waited for
       // (otherwise every tile pays a second memory round trip between the TMEM read and the store)
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         }
       }
       ptx::mbar_wait(&acc_full[e], use & 1);
+      tl_mark(tl, e, n, 1);
       ptx::tcgen05_fence_after();
 #pragma unroll 1
       for (int nbi = 0; nbi < NB; ++nbi) {
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
           }
         }
       }
+      tl_mark(tl, e, n, 2);
     }
   } else if (warp == 8) {
     ptx::setmaxnreg_dec<104>();
@@ -203,7 +207,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
       for (int kbi = 0; kbi < KB; ++kbi) {
         const int kb = (kbi + static_cast<int>(blockIdx.x)) % KB;      // the producers' order (see there)
         const int seq = n * KB + kbi, slot = seq % L::NSLOT, suse = seq / L::NSLOT;
+        if (lane == 0) tl_mark(a.timeline, 2, seq, 0);
         ptx::mbar_wait(&full[slot], suse & 1);
+        if (lane == 0) tl_mark(a.timeline, 2, seq, 1);
         ptx::tcgen05_fence_after();
         if (ptx::elect_one()) {
           const int pa_[3] = {1, 0, 0}, pb_[3] = {0, 1, 0};        // (A plane, B plane): lo.hi, hi.lo, hi.hi
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
           if (kbi == KB - 1) ptx::umma_commit(&acc_full[acc]);
         }
         __syncwarp();
+        if (lane == 0) tl_mark(a.timeline, 2, seq, 2);
       }
     }
   } else {
@@ -239,6 +246,8 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         const uint32_t slot_s = ptx::smem_u32(ring + slot * L::SLOT_BYTES);
         // every load of this warp's share of the block first (up to twelve 16-byte loads per lane), then the slot
         // wait: the loads do not touch the slot
+        long long* tlp = (gw == 0 && lane == 0) ? a.timeline : nullptr;
+        tl_mark(tlp, 3, seq, 0);
         float u[GPW][2][8];                             // one 32-byte load (LDG.256) per lane and chunk
 #pragma unroll
         for (int i = 0; i < GPW; ++i) {
@@ -251,10 +260,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
             if (g < 16 && row < a.n_rows) ptx::ldg256_coherent(xp + row * xld + (cq + 4 * j) * 8, u[i][j]);
           }
         }
+        tl_mark(tlp, 3, seq, 1);
         if (suse >= 1) ptx::mbar_wait(&empty[slot], (suse - 1) & 1);
+        tl_mark(tlp, 3, seq, 2);
 #pragma unroll
         for (int i = 0; i < GPW; ++i) {
           const int g = gw + TR_PRODUCERS * i;
+          if (i == 1) tl_mark(tlp, 3, seq, 3);            // the first group's data has arrived and is converted
           if (g < 16) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -269,6 +281,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) tc_rowgemm_kernel(const RowGemm
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&full[slot]);
+        tl_mark(tlp, 3, seq, 4);
       }
     }
   }

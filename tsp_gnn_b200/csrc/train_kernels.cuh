@@ -30,6 +30,7 @@ struct RowGemmArgs {
   const float* mask;         // EPI_MASK: multiply by (mask[row * mld + col] > 0); one 64-column block (N == 64)
   int mld;
   int64_t n_rows;
+  long long* timeline;       // optional clock64() trace of tc_rowgemm_kernel's roles (tools/timeline_train.py), nullptr in production
 };
 
 constexpr int EPI_NONE = 0, EPI_RELU = 1, EPI_MASK = 2, EPI_ACCUM = 4;
