@@ -94,6 +94,10 @@ struct K2Args {
   const uint8_t* ent_row;  // [tilesE][256] row of the tile
   const int32_t* ent_v;    // [tilesE][256] vertex it adds to, -1 = padding
   unsigned int* zero_word; // optional: cleared by this launch (grid barrier counter of the persistent kernel that follows)
+  // Training forward (optional): the hidden activations of the EDGE chain (layers 1-3 of E_msg_V, post-ReLU) as bf16
+  // hi / lo tile images, [edge tile][layer 0..2][hi 16 KB | lo 16 KB] in the layout of the h planes -- exactly the
+  // operand image tc_layer_reverse_kernel needs for a_{l-1}, so the reverse pass neither recomputes nor converts them
+  uint8_t* act_out;
   long long* timeline;
   int tl_slot;
 };
@@ -1106,6 +1110,12 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
           if (feeds_mma) {
             ptx::sts128(nxt + ch * 2048, make_uint4(hi[0], hi[1], hi[2], hi[3]));
             if (HP == 2) ptx::sts128(nxt + PLANE_BYTES + ch * 2048, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          }
+          if (ROLE == 1 && HP == 2 && a.act_out != nullptr) {
+            // coalesced: a warp writes 512 contiguous bytes per store (thread = row, 16 bytes per chunk)
+            uint4* g = reinterpret_cast<uint4*>(a.act_out + (static_cast<int64_t>(t0 + n) * 3 + l) * (2 * PLANE_BYTES)) + r;
+            g[ch * 128] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            g[1024 + ch * 128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
         if (feeds_mma) ptx::fence_proxy_async_smem();

@@ -548,6 +548,11 @@ struct LayerRevArgs {
   int dld;
   const float* a;        // a_{l-1} [rows, 64]: input of layer l
   int ald;
+  // alternative to `a`: a_{l-1} as bf16 hi / lo tile images written by the training forward (K2Args::act_out),
+  // tile t at a_img + t * a_img_stride: [hi 16 KB | lo 16 KB].  The stage takes them by bulk copy (no conversion) and
+  // the ReLU mask is read from the hi plane (a > 0 <=> bf16(a) != 0 for a ReLU output).
+  const uint8_t* a_img;
+  int64_t a_img_stride;
   float* y;              // d_{l-1} [rows, 64]
   int yld;
   const float* w;        // W_l stored [w_rows = inputs][w_cols = outputs], leading dimension ldw
@@ -631,7 +636,19 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
       const int acc = n & 1, use = n >> 1;
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS + warp * 32 + tq1;   // + 8 m
       float2 pre[4][8];           // ReLU mask source a_{l-1} (MASK) or the previous output (ACCUM), before the wait
-      if (EPI & (EPI_MASK | EPI_ACCUM)) {
+      if ((EPI & EPI_MASK) && a.a_img != nullptr) {
+        // the mask from the hi plane of the image: chunk k, row, columns 2 tq0, 2 tq0 + 1 = one 32-bit word
+        const uint8_t* img = a.a_img + static_cast<int64_t>(t0 + n) * a.a_img_stride;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int rt = warp * 32 + tq1 + 8 * m;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(img + k * 2048 + rt * 16 + tq0 * 4));
+            pre[m][k] = make_float2((w2 & 0xffffu) ? 1.f : 0.f, (w2 >> 16) ? 1.f : 0.f);
+          }
+        }
+      } else if (EPI & (EPI_MASK | EPI_ACCUM)) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const int64_t row = row0 + 8 * m;
@@ -715,12 +732,18 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
       const uint32_t ds = ptx::smem_u32(smem + L::STAGE_OFF + st * L::STAGE), as = ds + 2 * L::DP;
       // the tile's sixteen 16-byte loads per lane are requested before the stage is waited for
+      // with a_img only the d tasks are left (two quads per row group): the a image comes by bulk copy
+      const int quads_eff = (a.a_img != nullptr) ? 2 : quads;
       float u[8][8];                                    // one 32-byte load (LDG.256) per task and lane
       uint32_t dst[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int task = pw + 8 * i;
-        const int g = task / quads, qd = task % quads;
+        if (task >= 16 * quads_eff) {
+          dst[i] = 0u;
+          continue;
+        }
+        const int g = task / quads_eff, qd = task % quads_eff;
         const int64_t row = row0 + g * 8 + r8;
         const int chunk = (qd & 1) * 4 + cq;
         const float* p = (qd < 2) ? a.d + row * a.dld + chunk * 8 : a.a + row * a.ald + chunk * 8;
@@ -731,8 +754,16 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
       }
       static_assert(ntask == 64, "eight producer warps, eight tasks each");
       if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
+      if (a.a_img != nullptr && pw == 0 && lane == 0) {
+        // hi plane -> chunks 0..7 of the a image's hi plane, lo plane likewise (chunks 8..15 stay ones / zeros)
+        const uint8_t* img = a.a_img + static_cast<int64_t>(t0 + n) * a.a_img_stride;
+        ptx::mbar_expect_tx(&full[st], 2 * PLANE_BYTES);
+        ptx::bulk_g2s(smem + L::STAGE_OFF + st * L::STAGE + 2 * L::DP, img, PLANE_BYTES, &full[st]);
+        ptx::bulk_g2s(smem + L::STAGE_OFF + st * L::STAGE + 2 * L::DP + L::AP, img + PLANE_BYTES, PLANE_BYTES, &full[st]);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        if (dst[i] == 0u) continue;
         uint4 hi, lo;
         split8(u[i], hi, lo);
         const bool is_d = dst[i] < as;

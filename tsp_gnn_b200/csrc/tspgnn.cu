@@ -149,6 +149,13 @@ struct tspgnn_ctx {
   float *mV2 = nullptr, *xV2 = nullptr;               // second halves of the message double buffers
   unsigned int* d_gridctr = nullptr;                  // grid barrier counter of the persistent fused kernel
   bool train_tc = true;                               // reverse pass: tcgen05 row GEMMs (tensor-core modes); false: fp32 CUDA-core tiles
+  // training forward: hidden activations of the edge message MLP as operand images (K2Args::act_out),
+  // [timestep][edge tile][layer 0..2][32 KB]; cur_act_out = where the next message launch writes (nullptr: nowhere)
+  uint8_t* act_snap = nullptr;
+  int64_t act_cap = 0;
+  uint8_t* cur_act_out = nullptr;
+  bool act_images = true;                             // tspgnn_set_option("act_images", 0): recompute them in the reverse pass
+  int act_T = -1;                                     // timesteps of the last training forward that wrote them (-1: none)
   float* d_gpart = nullptr;                           // [gpart_slots][total] per-CTA partial gradients of tc_xtdy_kernel
   int gpart_slots = 0;
   int64_t gpart_stride = 0;                           // floats between slots (blob size rounded up to 32)
@@ -290,6 +297,7 @@ extern "C" int tspgnn_create(int d, int mode, int device, tspgnn_handle* out) {
       return TSPGNN_E_CUDA;
     }
     CUDA_TRY(cudaMemset(h->d_gridctr, 0, sizeof(unsigned int)));
+    if (const char* env = std::getenv("TSPGNN_ACT_IMAGES")) h->act_images = std::atoi(env) != 0;   // A/B switch (tools)
   }
   *out = h;
   return 0;
@@ -312,6 +320,7 @@ extern "C" int tspgnn_destroy(tspgnn_handle h) {
   void* fp[] = {h->d_wl_pair[0], h->d_wl_pair[1], h->d_wm_pair[0], h->d_wm_pair[1], h->mV2, h->xV2, h->d_gridctr, h->d_ent_row, h->d_ent_v, h->d_gpart};
   for (void* p : fp)
     if (p) cudaFree(p);
+  if (h->act_snap) cudaFree(h->act_snap);
   void* tp[] = {h->snap, h->d_grads, h->d_adam_m, h->d_adam_v, h->d_scal, h->d_y, h->d_dvote, h->d_wlstm_vfold, h->d_deg, h->d_lntab, h->d_biastab};
   for (void* p : tp)
     if (p) cudaFree(p);
@@ -333,6 +342,7 @@ extern "C" int tspgnn_set_option(tspgnn_handle h, const char* name, double value
   if (key == "fused") h->fused = value != 0.0;
   else if (key == "train_tc") h->train_tc = value != 0.0;
   else if (key == "train_graph") h->bwd_graphs = value != 0.0;
+  else if (key == "act_images") h->act_images = value != 0.0;
   else if (key == "v_pair_weight" && value > 0.0) h->v_pair_weight = value;
   else if (key == "dbg") h->dbg = static_cast<int>(value);
   else return fail(TSPGNN_E_INVALID, "unknown option '%s' (or bad value %g)", name, value);
@@ -780,6 +790,7 @@ static int tc_launch_k2(tspgnn_ctx* h, cudaStream_t s, bool vote, bool fold, lon
   a.ent_row = h->d_ent_row;
   a.ent_v = h->d_ent_v;
   a.zero_word = h->d_gridctr;
+  a.act_out = vote ? nullptr : h->cur_act_out;
   a.stateE = h->stateE;
   a.stateV = h->stateV;
   a.wE = vote ? h->d_wmlp[2] : h->d_wmlp[1];
