@@ -1,5 +1,7 @@
 """clock64() trace of the warp roles of the reverse pass's tcgen05 row GEMM on edge-sized matrices (north-star size).
-usage: python tools/timeline_train.py [4|5|6] [cta,cta,...]    4 = 64-wide layer, 5 = dz.K^T, 6 = z = [x,h].K
+usage: python tools/timeline_train.py [4|5|6|7] [cta,cta,...]    4 = 64-wide layer, 5 = dz.K^T, 6 = z = [x,h].K,
+       7 = tc_layer_reverse_kernel (epilogue: 0 tile start, 1 mask requested, 2 accumulator ready, 3 stores issued;
+           mma: 0 start, 1 stage full, 2 accumulator free, 3 issued; producer 0: 0 start, 1 loads issued, 2 stage free, 4 published)
 events  epilogue WG: 0 tile start, 1 accumulator ready, 2 stores issued
         mma        : 0 waits for the operand block, 1 block ready, 2 MMAs issued (per k-block)
         producer 0 : 0 block start, 1 loads issued, 2 slot free, 3 first group converted (data arrived), 4 block published"""

@@ -553,6 +553,7 @@ struct LayerRevArgs {
   // the ReLU mask is read from the hi plane (a > 0 <=> bf16(a) != 0 for a ReLU output).
   const uint8_t* a_img;
   int64_t a_img_stride;
+  long long* timeline;   // optional clock64() trace (tools/timeline_train.py), nullptr in production
   float* y;              // d_{l-1} [rows, 64]
   int yld;
   const float* w;        // W_l stored [w_rows = inputs][w_cols = outputs], leading dimension ldw
@@ -560,6 +561,16 @@ struct LayerRevArgs {
   float* pblob;          // per-CTA partial gradients (see tc_xtdy_kernel)
   int64_t total, dw_off, db_off;
   int64_t n_rows;
+  // d_l and d_{l-1} as operand images too (one per 128-row tile: [hi 16 KB | lo 16 KB], tile t at base + t * stride):
+  // inside an MLP's reverse chain the layer kernels hand d from one to the next in this form.  The consumer takes it
+  // by bulk copy (no producer work); the epilogue writes it with 4-byte stores that cover one full 128-byte line
+  // per warp instruction (8 rows x 16 bytes of a chunk), where the row-major fp32 form touches 8 lines for 256
+  // bytes -- the epilogue's load/store wavefronts bounded the kernel (tools/timeline_train.py 7).  Rows past n_rows
+  // are written as zeros.
+  const uint8_t* d_img;
+  int64_t d_img_stride;
+  uint8_t* y_img;
+  int64_t y_img_stride;
 };
 
 struct LRSmem {
@@ -632,7 +643,9 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
   if (warp < 4) {
     // ---- epilogue: d_{l-1} tile ---------------------------------------------------------------------------------
     const int tq0 = lane & 3, tq1 = lane >> 2;
+    long long* tl = (warp == 0 && lane == 0) ? a.timeline : nullptr;
     for (int n = 0; n < ntiles; ++n) {
+      tl_mark(tl, 0, n, 0);
       const int acc = n & 1, use = n >> 1;
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS + warp * 32 + tq1;   // + 8 m
       float2 pre[4][8];           // ReLU mask source a_{l-1} (MASK) or the previous output (ACCUM), before the wait
@@ -662,13 +675,39 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
           }
         }
       }
+      tl_mark(tl, 0, n, 1);
       ptx::mbar_wait(&d1_full[acc], use & 1);
+      tl_mark(tl, 0, n, 2);
       ptx::tcgen05_fence_after();
       float qa[32], qb[32];
       ptx::tmem_ld_quad64(tmem + (static_cast<uint32_t>(warp * 32) << 16) + acc * 64, qa, qb);
       ptx::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&d1_empty[acc]);
+      if (a.y_img != nullptr) {
+        // d_{l-1} as hi / lo image: word (chunk k, row, column pair tq0); a warp store covers 128 contiguous bytes
+        uint8_t* img = a.y_img + static_cast<int64_t>(t0 + n) * a.y_img_stride;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int rt = warp * 32 + tq1 + 8 * m;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int ix = 4 * k + 2 * (m & 1);
+            float2 v = make_float2(((m < 2) ? qa : qb)[ix], ((m < 2) ? qa : qb)[ix + 1]);
+            if (EPI & EPI_MASK) {
+              v.x = (pre[m][k].x > 0.f) ? v.x : 0.f;
+              v.y = (pre[m][k].y > 0.f) ? v.y : 0.f;
+            }
+            uint32_t hi, lo;
+            ptx::split_bf16x2(v.x, v.y, hi, lo);
+            uint32_t* w = reinterpret_cast<uint32_t*>(img + k * 2048 + rt * 16 + tq0 * 4);
+            w[0] = hi;
+            w[PLANE_BYTES / 4] = lo;
+          }
+        }
+        tl_mark(tl, 0, n, 3);
+        continue;
+      }
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int64_t row = row0 + 8 * m;
@@ -690,6 +729,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
           }
         }
       }
+      tl_mark(tl, 0, n, 3);
     }
     // ---- the CTA's weight-gradient partial: lane = input feature, 64 output columns ---------------------------------
     if (ntiles > 0) {
@@ -729,11 +769,16 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
     constexpr int quads = 4, ntask = 16 * quads;          // per 8-row group: d (2 quads of 4 chunks), a (2)
     for (int n = 0; n < ntiles; ++n) {
       const int st = n & 1, use = n >> 1;
+      long long* tlp = (pw == 0 && lane == 0) ? a.timeline : nullptr;
+      tl_mark(tlp, 3, n, 0);
       const int64_t row0 = static_cast<int64_t>(t0 + n) * TILE_ROWS;
       const uint32_t ds = ptx::smem_u32(smem + L::STAGE_OFF + st * L::STAGE), as = ds + 2 * L::DP;
       // the tile's sixteen 16-byte loads per lane are requested before the stage is waited for
       // with a_img only the d tasks are left (two quads per row group): the a image comes by bulk copy
-      const int quads_eff = (a.a_img != nullptr) ? 2 : quads;
+      // operands that come as images are bulk-copied below: only the row-major ones are left as tasks
+      static_assert(quads == 4, "d tasks are quads 0-1, a tasks quads 2-3");
+      const int qoff = (a.d_img != nullptr) ? 2 : 0;
+      const int quads_eff = quads - ((a.d_img != nullptr) ? 2 : 0) - ((a.a_img != nullptr) ? 2 : 0);
       float u[8][8];                                    // one 32-byte load (LDG.256) per task and lane
       uint32_t dst[8];
 #pragma unroll
@@ -743,7 +788,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
           dst[i] = 0u;
           continue;
         }
-        const int g = task / quads_eff, qd = task % quads_eff;
+        const int g = task / quads_eff, qd = task % quads_eff + qoff;
         const int64_t row = row0 + g * 8 + r8;
         const int chunk = (qd & 1) * 4 + cq;
         const float* p = (qd < 2) ? a.d + row * a.dld + chunk * 8 : a.a + row * a.ald + chunk * 8;
@@ -753,13 +798,23 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
         if (row < a.n_rows) ptx::ldg256_coherent(p, u[i]);
       }
       static_assert(ntask == 64, "eight producer warps, eight tasks each");
+      tl_mark(tlp, 3, n, 1);
       if (use >= 1) ptx::mbar_wait(&empty[st], (use - 1) & 1);
-      if (a.a_img != nullptr && pw == 0 && lane == 0) {
-        // hi plane -> chunks 0..7 of the a image's hi plane, lo plane likewise (chunks 8..15 stay ones / zeros)
-        const uint8_t* img = a.a_img + static_cast<int64_t>(t0 + n) * a.a_img_stride;
-        ptx::mbar_expect_tx(&full[st], 2 * PLANE_BYTES);
-        ptx::bulk_g2s(smem + L::STAGE_OFF + st * L::STAGE + 2 * L::DP, img, PLANE_BYTES, &full[st]);
-        ptx::bulk_g2s(smem + L::STAGE_OFF + st * L::STAGE + 2 * L::DP + L::AP, img + PLANE_BYTES, PLANE_BYTES, &full[st]);
+      tl_mark(tlp, 3, n, 2);
+      if (pw == 0 && lane == 0) {
+        uint8_t* stage = smem + L::STAGE_OFF + st * L::STAGE;
+        if (a.a_img != nullptr) {
+          // hi plane -> chunks 0..7 of the a image's hi plane, lo plane likewise (chunks 8..15 stay ones / zeros)
+          const uint8_t* img = a.a_img + static_cast<int64_t>(t0 + n) * a.a_img_stride;
+          ptx::mbar_expect_tx(&full[st], 2 * PLANE_BYTES);
+          ptx::bulk_g2s(stage + 2 * L::DP, img, PLANE_BYTES, &full[st]);
+          ptx::bulk_g2s(stage + 2 * L::DP + L::AP, img + PLANE_BYTES, PLANE_BYTES, &full[st]);
+        }
+        if (a.d_img != nullptr) {
+          const uint8_t* img = a.d_img + static_cast<int64_t>(t0 + n) * a.d_img_stride;
+          ptx::mbar_expect_tx(&full[st], 2 * PLANE_BYTES);
+          ptx::bulk_g2s(stage, img, 2 * PLANE_BYTES, &full[st]);       // hi | lo = the d image of the stage (DP apart)
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -778,6 +833,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&full[st]);
+      tl_mark(tlp, 3, n, 4);
     }
   } else {
     // ---- MMA issuer -----------------------------------------------------------------------------------------------
@@ -786,8 +842,11 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
     const uint64_t wdesc = ptx::umma_desc_k_nosw(ptx::smem_u32(wsm), 64 * 16, 128);
     for (int n = 0; n < ntiles; ++n) {
       const int st = n & 1, use = n >> 1;
+      if (lane == 0) tl_mark(a.timeline, 2, n, 0);
       ptx::mbar_wait(&full[st], use & 1);
+      if (lane == 0) tl_mark(a.timeline, 2, n, 1);
       if (use >= 1) ptx::mbar_wait(&d1_empty[st], (use - 1) & 1);
+      if (lane == 0) tl_mark(a.timeline, 2, n, 2);
       ptx::tcgen05_fence_after();
       if (ptx::elect_one()) {
         const uint32_t ds = ptx::smem_u32(smem + L::STAGE_OFF + st * L::STAGE), as = ds + 2 * L::DP;
@@ -814,6 +873,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) tc_layer_reverse_kernel(const L
         if (n == ntiles - 1) ptx::umma_commit(d2_full);
       }
       __syncwarp();
+      if (lane == 0) tl_mark(a.timeline, 2, n, 3);
     }
   }
   ptx::tcgen05_fence_before();

@@ -154,6 +154,7 @@ struct tspgnn_ctx {
   uint8_t* act_snap = nullptr;
   int64_t act_cap = 0;
   uint8_t* cur_act_out = nullptr;
+  bool d_images = true;                               // mlp_reverse hands d between its layer kernels as operand images ("d_images")
   bool act_images = true;                             // tspgnn_set_option("act_images", 0): recompute them in the reverse pass
   int act_T = -1;                                     // timesteps of the last training forward that wrote them (-1: none)
   float* d_gpart = nullptr;                           // [gpart_slots][total] per-CTA partial gradients of tc_xtdy_kernel
@@ -298,6 +299,7 @@ extern "C" int tspgnn_create(int d, int mode, int device, tspgnn_handle* out) {
     }
     CUDA_TRY(cudaMemset(h->d_gridctr, 0, sizeof(unsigned int)));
     if (const char* env = std::getenv("TSPGNN_ACT_IMAGES")) h->act_images = std::atoi(env) != 0;   // A/B switch (tools)
+    if (const char* env = std::getenv("TSPGNN_D_IMAGES")) h->d_images = std::atoi(env) != 0;
   }
   *out = h;
   return 0;
@@ -343,6 +345,7 @@ extern "C" int tspgnn_set_option(tspgnn_handle h, const char* name, double value
   else if (key == "train_tc") h->train_tc = value != 0.0;
   else if (key == "train_graph") h->bwd_graphs = value != 0.0;
   else if (key == "act_images") h->act_images = value != 0.0;
+  else if (key == "d_images") h->d_images = value != 0.0;
   else if (key == "v_pair_weight" && value > 0.0) h->v_pair_weight = value;
   else if (key == "dbg") h->dbg = static_cast<int>(value);
   else return fail(TSPGNN_E_INVALID, "unknown option '%s' (or bad value %g)", name, value);
@@ -1202,6 +1205,8 @@ extern "C" int tspgnn_time_kernel(tspgnn_handle h, int which, int iters, float* 
 namespace {
 template <int KB, int NB, bool TRANS, int EPI>
 int launch_tc_rowgemm(tspgnn_ctx* h, cudaStream_t s, const RowGemmArgs& a);      // train_host.inc
+template <int EPI>
+int launch_layer_reverse(tspgnn_ctx* h, cudaStream_t s, const LayerRevArgs& a);
 }
 
 // Development aid (tools/timeline.py): one launch of K2 (which = 1) or K1 (which = 0) with the
@@ -1218,7 +1223,28 @@ extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_
   CUDA_TRY(cudaMalloc(&d, need * 8));
   CUDA_TRY(cudaMemsetAsync(d, 0, need * 8, s));
   int rc;
-  if (which >= 4 && which <= 6) {
+  if (which == 7) {
+    // one layer of an MLP's reverse chain (tc_layer_reverse_kernel, ReLU mask) on edge-sized scratch matrices
+    float *X = nullptr;
+    const int64_t rows = h->nE;
+    CUDA_TRY(cudaMalloc(&X, rows * 3 * D * sizeof(float)));
+    CUDA_TRY(cudaMemsetAsync(X, 0, rows * 3 * D * sizeof(float), s));
+    if (!h->d_gpart) {
+      h->gpart_slots = h->num_sms;
+      h->gpart_stride = (h->po.total + 31) & ~static_cast<int64_t>(31);
+      if (dev_alloc(&h->d_gpart, static_cast<int64_t>(h->gpart_slots) * h->gpart_stride)) return TSPGNN_E_CUDA;
+    }
+    LayerRevArgs r = {};
+    r.d = X; r.dld = D; r.a = X + rows * D; r.ald = D; r.y = X + 2 * rows * D; r.yld = D;
+    r.w = h->d_params + h->po.msg_w[1][1]; r.ldw = D; r.w_rows = D; r.w_cols = D;
+    r.pblob = h->d_gpart; r.total = h->gpart_stride; r.dw_off = h->po.msg_w[1][1]; r.db_off = h->po.msg_b[1][1];
+    r.n_rows = rows;
+    r.timeline = d;
+    rc = launch_layer_reverse<EPI_MASK>(h, s, r);
+    if (!rc) rc = launch_layer_reverse<EPI_MASK>(h, s, r);
+    cudaStreamSynchronize(s);
+    cudaFree(X);
+  } else if (which >= 4 && which <= 6) {
     // reverse-pass row GEMM on edge-sized scratch matrices (contents irrelevant): 4 = a 64-wide layer (KB 1, NB 1),
     // 5 = dz . K^T (KB 4, NB 2, transposed weights), 6 = z = [x, h] . K (KB 2, NB 4)
     float *X = nullptr, *Y = nullptr;
