@@ -1223,7 +1223,7 @@ extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_
   CUDA_TRY(cudaMalloc(&d, need * 8));
   CUDA_TRY(cudaMemsetAsync(d, 0, need * 8, s));
   int rc;
-  if (which == 7) {
+  if (which == 7 || which == 8) {          // 8: every operand as an image (bulk copies in, image out)
     // one layer of an MLP's reverse chain (tc_layer_reverse_kernel, ReLU mask) on edge-sized scratch matrices
     float *X = nullptr;
     const int64_t rows = h->nE;
@@ -1240,6 +1240,11 @@ extern "C" int tspgnn_debug_timeline(tspgnn_handle h, int which, long long* out_
     r.pblob = h->d_gpart; r.total = h->gpart_stride; r.dw_off = h->po.msg_w[1][1]; r.db_off = h->po.msg_b[1][1];
     r.n_rows = rows;
     r.timeline = d;
+    if (which == 8) {
+      r.d_img = reinterpret_cast<const uint8_t*>(X); r.d_img_stride = 2 * PLANE_BYTES;
+      r.a_img = reinterpret_cast<const uint8_t*>(X + rows * D); r.a_img_stride = 2 * PLANE_BYTES;
+      r.y_img = reinterpret_cast<uint8_t*>(X + 2 * rows * D); r.y_img_stride = 2 * PLANE_BYTES;
+    }
     rc = launch_layer_reverse<EPI_MASK>(h, s, r);
     if (!rc) rc = launch_layer_reverse<EPI_MASK>(h, s, r);
     cudaStreamSynchronize(s);
