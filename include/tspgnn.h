@@ -60,7 +60,12 @@ int tspgnn_get_mode(tspgnn_handle h);
  *   "v_pair_weight": relative cost of a vertex tile pair used to split the clusters of the fused kernel.
  *   "train_tc" (default 1): reverse-pass contractions on tcgen05 (tensor-core modes); 0 = fp32 CUDA-core kernels.
  *   "train_graph" (default 1): replay the reverse pass from a CUDA graph once the same tspgnn_backward call
- *       (same plan geometry, buffers and timestep count) has been seen twice in a row. */
+ *       (same plan geometry, buffers and timestep count) has been seen twice in a row.
+ *   "act_images" (default 1, bf16x3 mode): tspgnn_train_forward keeps the hidden activations of the edge message MLP
+ *       as bf16 hi / lo operand images (75 MB per timestep at the north-star batch) and the reverse pass bulk-copies
+ *       them instead of recomputing the three layers per timestep; 0 = recompute.
+ *   "d_images" (default 1): inside an MLP's reverse chain d travels between the layer kernels as an operand image;
+ *       0 = row-major fp32. */
 int tspgnn_set_option(tspgnn_handle h, const char* name, double value);
 
 /* Replaces tf.global_variables_initializer() / Saver.restore (train.py:210, util.py:17):

@@ -152,6 +152,38 @@ def test_tensor_core_reverse_pass_matches_fp32_reverse_pass(sizes, T):
     print("tensor-core vs fp32 reverse pass: worst tensor error %.2e of scale" % worst)
 
 
+@pytest.mark.parametrize("sizes,T", [([9, 14, 11, 20, 33, 7], 6), ([40] * 8, 4)])
+def test_operand_images_of_the_reverse_pass_match_the_recomputed_row_major_forms(sizes, T):
+    """Options act_images / d_images (include/tspgnn.h): the edge message MLP's activations kept as bf16 hi / lo
+    operand images by the training forward and d handed between the layer kernels as images, against the same
+    tensor-core reverse pass with recomputed activations and row-major fp32 d.  Both forms feed the MMAs the same
+    hi / lo operands up to the rounding of the recompute (2^-16 relative), and the ReLU mask read from the hi plane
+    equals the fp32 one; ragged sizes exercise the zero rows of partial tiles."""
+    from tsp_gnn_b200.engine import Engine
+    EV, W, C, y, nv, ne = inst.synth_batch(sizes, seed=13)
+    params = orc.init_params(64, seed=6, perturb_ln=True)
+    blobs = []
+    for flags in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        eng = Engine(64, "bf16x3", 0)
+        eng.set_params(params)
+        eng.set_option("act_images", flags[0])
+        eng.set_option("d_images", flags[1])
+        eng.plan(nv, ne, EV.src, EV.dst)
+        loss, logits, blob = run_backward(eng, W, C, y, T)
+        eng.close()
+        blobs.append(blob.astype(np.float64))
+    ref = blobs[1]
+    for flags, b in zip(((1, 1), (1, 0), (0, 1)), (blobs[0], blobs[2], blobs[3])):
+        cos = float(np.dot(b, ref) / (np.linalg.norm(b) * np.linalg.norm(ref)))
+        ta, tr = P.unflatten(b.astype(np.float32)), P.unflatten(ref.astype(np.float32))
+        rels = [float(np.abs(ta[k] - tr[k]).max()) / (float(np.abs(tr[k]).max()) + 1e-30) for k in tr]
+        print("act_images=%d d_images=%d: cosine %.9f, median / worst tensor error %.2e / %.2e of scale"
+              % (flags[0], flags[1], cos, float(np.median(rels)), max(rels)))
+        assert cos >= 1.0 - 1e-5, (flags, cos)
+        assert float(np.median(rels)) <= 2e-3, (flags, float(np.median(rels)))
+        assert max(rels) <= 5e-2, (flags, max(rels))
+
+
 @pytest.mark.parametrize("mode", ["simt", "bf16x3"])
 @pytest.mark.parametrize("name", ["ref_train_tiny", "ref_train_sparse"])
 def test_train_step_matches_reference_training_graph_fixtures(name, mode):
