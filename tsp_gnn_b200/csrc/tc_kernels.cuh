@@ -1114,8 +1114,10 @@ __device__ __forceinline__ void k2_chain(const K2Args& a, uint8_t* slots, uint64
           if (ROLE == 1 && HP == 2 && a.act_out != nullptr) {
             // coalesced: a warp writes 512 contiguous bytes per store (thread = row, 16 bytes per chunk)
             uint4* g = reinterpret_cast<uint4*>(a.act_out + (static_cast<int64_t>(t0 + n) * 3 + l) * (2 * PLANE_BYTES)) + r;
-            g[ch * 128] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            g[1024 + ch * 128] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            // streaming stores: 75 MB per timestep that nobody reads before the reverse pass must not push the
+            // recurrent state (54 MB) out of the L2
+            __stcs(g + ch * 128, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            __stcs(g + 1024 + ch * 128, make_uint4(lo[0], lo[1], lo[2], lo[3]));
           }
         }
         if (feeds_mma) ptx::fence_proxy_async_smem();
@@ -1483,10 +1485,10 @@ __global__ void __launch_bounds__(256) tc_unpack_state_kernel(const uint8_t* __r
       x0 += __uint_as_float(lo << 16);
       x1 += __uint_as_float(lo & 0xFFFF0000u);
     }
-    *reinterpret_cast<float2*>(h + row * D + col) = make_float2(x0, x1);
+    __stcs(reinterpret_cast<float2*>(h + row * D + col), make_float2(x0, x1));   // streaming: the copy is not read back soon
   }
-  if (c) *reinterpret_cast<float2*>(c + row * D + col) =
-      *reinterpret_cast<const float2*>(tile + HP * PLANE_BYTES + ct_off(r, col));
+  if (c) __stcs(reinterpret_cast<float2*>(c + row * D + col),
+                *reinterpret_cast<const float2*>(tile + HP * PLANE_BYTES + ct_off(r, col)));
 }
 
 }  // namespace tspgnn
